@@ -1,0 +1,288 @@
+"""CPU oracle for the block-wise SignRound tuning loop.
+
+TEST INFRASTRUCTURE ONLY (see oracle/qdq.py header).  Restates, with torch-CPU autograd:
+  * auto_round/wrapper.py:62-293, :517-565      WrapperLinear (tunable V / min_scale / max_scale, qdq + F.linear)
+  * auto_round/wrapper.py:345-468               unwrapper (bake best params, attach scale/zp)
+  * auto_round/algorithms/quantization/sign_round/quantizer.py:311-552   quantize_block (the 200-iter loop)
+  * auto_round/algorithms/quantization/sign_round/quantizer.py:127-158   masked MSE loss
+  * auto_round/algorithms/quantization/sign_round/sign_sgd.py:356-389    sign-SGD update
+  * auto_round/compressors/utils.py:388-438     IndexSampler (python `random`, global state)
+  * auto_round/compressors/utils.py:109-172     block_forward (autocast(bf16) around the HF layer)
+Pinned by tests/golden/block_*.pt: loss curves / best iteration / final qdq weights / scales produced
+by the unmodified reference on tiny random-init blocks (oracle/gen_golden.py), which this module must
+reproduce bit-for-bit on CPU (same torch ops in the same order).
+"""
+from __future__ import annotations
+
+import random
+from dataclasses import dataclass, field
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import qdq as Q
+
+
+@dataclass
+class LayerScheme:
+    bits: int = 4
+    group_size: int = 128
+    sym: bool = True
+    data_type: str = "int"            # "int" | "mx_fp" | "nv_fp"
+    scale_dtype: torch.dtype = torch.float16
+
+    @property
+    def qdq_name(self) -> str:
+        if self.data_type == "int":
+            return "int_sym" if self.sym else "int_asym"
+        return {"mx_fp": "mx_fp4", "nv_fp": "nv_fp4"}[self.data_type]
+
+
+class IndexSampler:
+    """compressors/utils.py:388-438.  Consumes the GLOBAL python `random` state, like the reference."""
+
+    def __init__(self, nsamples: int, batch_size: int):
+        if batch_size <= 0 or batch_size > nsamples:
+            raise ValueError("batch_size must be > 0 and <= nsamples")
+        self.nsamples, self.batch_size, self.index = nsamples, batch_size, 0
+        self.indices = list(range(nsamples))
+        random.shuffle(self.indices)
+
+    def next_batch(self):
+        if self.index + self.batch_size > self.nsamples:
+            random.shuffle(self.indices)
+            self.index = 0
+        out = self.indices[self.index: self.index + self.batch_size]
+        self.index += self.batch_size
+        return out
+
+
+class ReplaySampler:
+    """Feeds a recorded batch sequence (fixtures store what the reference's sampler produced)."""
+
+    def __init__(self, batches):
+        self.batches, self.i = [list(b) for b in batches], 0
+
+    def next_batch(self):
+        b = self.batches[self.i]
+        self.i += 1
+        return b
+
+
+class TunableLinear(nn.Module):
+    """WrapperLinear restated: same parameters, same per-forward in-place clamp, same qdq call."""
+
+    def __init__(self, linear: nn.Linear, scheme: LayerScheme, global_scale=None, minmax_bound=(0.0, 1.0)):
+        super().__init__()
+        self.linear, self.scheme, self.bound = linear, scheme, minmax_bound
+        w = linear.weight.data
+        groups, _, _ = Q.to_groups(w, scheme.group_size)
+        self.wmin = torch.clamp(groups.min(1)[0], max=0)
+        self.wmax = torch.clamp(groups.max(1)[0], min=0)
+        self.value = nn.Parameter(torch.zeros(groups.shape, dtype=torch.float32))
+        nscale = groups.shape[0]
+        self.min_scale = nn.Parameter(torch.ones(nscale, dtype=torch.float32))
+        self.max_scale = nn.Parameter(torch.ones(nscale, dtype=torch.float32))
+        self.q_scale_thresh = 1e-8 if scheme.scale_dtype == torch.float32 else 1e-5
+        self.global_scale = None
+        if scheme.data_type == "nv_fp":
+            self.global_scale = global_scale if global_scale is not None else Q.nv_global_scale(w)
+        self.params = {"value": self.value, "min_scale": self.min_scale, "max_scale": self.max_scale}
+
+    def qdq(self, value, min_scale, max_scale):
+        lo, hi = self.bound
+        min_scale.data.clamp_(lo, hi)
+        max_scale.data.clamp_(lo, hi)
+        w, sc = self.linear.weight, self.scheme
+        name = sc.qdq_name
+        if name == "int_sym":
+            out = Q.int_sym(w, sc.bits, sc.group_size, value, min_scale, max_scale, self.wmin, self.wmax,
+                            sc.scale_dtype, self.q_scale_thresh)
+        elif name == "int_asym":
+            out = Q.int_asym(w, sc.bits, sc.group_size, value, min_scale, max_scale, self.wmin, self.wmax,
+                             sc.scale_dtype, self.q_scale_thresh)
+        elif name == "mx_fp4":
+            out = Q.mx_fp4(w, sc.group_size, value, max_scale)
+        else:
+            out = Q.nv_fp4(w, sc.group_size, value, self.global_scale, max_scale)
+        wq, scale, zp = out
+        return wq.to(w.dtype), scale, zp
+
+    def forward(self, x):
+        wq, _, _ = self.qdq(self.value, self.min_scale, self.max_scale)
+        return F.linear(x, wq, self.linear.bias)
+
+    @torch.no_grad()
+    def bake(self, best):
+        """unwrapper: qdq with the best params -> weight.data; attach scale / zp / weight_global_scale."""
+        best = best or {}
+        v = best.get("value", torch.tensor(0.0))
+        mn = best.get("min_scale", torch.tensor(1.0))
+        mx = best.get("max_scale", torch.tensor(1.0))
+        wq, scale, zp = self.qdq(v, mn, mx)
+        lin = self.linear
+        lin.weight.data.copy_(wq)
+        n = wq.shape[0]
+        lin.scale = scale.reshape(n, -1) if scale.numel() > 1 else scale.view(-1)
+        if isinstance(zp, torch.Tensor):
+            lin.zp = zp.reshape(n, -1) if zp.numel() > 1 else zp.view(-1)
+        else:
+            lin.zp = zp
+        if self.global_scale is not None:
+            lin.weight_global_scale = self.global_scale
+        return lin
+
+
+def wrap_block(block: nn.Module, scheme_of, nv_global_scales=None):
+    """wrapper_block (wrapper.py:774-828): every nn.Linear with bits <= 8 -> TunableLinear."""
+    wrapped = {}
+    for name, mod in list(block.named_modules()):
+        if type(mod) is nn.Linear:
+            sc = scheme_of(name, mod)
+            if sc is None or sc.bits > 8:
+                continue
+            gs = None if nv_global_scales is None else nv_global_scales.get(name)
+            tl = TunableLinear(mod, sc, gs)
+            parent = block
+            parts = name.split(".")
+            for p in parts[:-1]:
+                parent = getattr(parent, p)
+            setattr(parent, parts[-1], tl)
+            wrapped[name] = tl
+    return wrapped
+
+
+def unwrap_block(block: nn.Module, wrapped: dict, best: dict):
+    for name, tl in wrapped.items():
+        lin = tl.bake(best.get(name))
+        parent = block
+        parts = name.split(".")
+        for p in parts[:-1]:
+            parent = getattr(parent, p)
+        setattr(parent, parts[-1], lin)
+
+
+SHARED_KEYS = ("position_ids", "cache_position", "position_embeddings", "cu_seqlens")  # utils/common.py:676
+
+
+def select_batch(inputs, others: dict, idx):
+    """BlockForwardRunner._select_batch (algorithms/block_runner.py:368-422): per-sample lists are
+    concatenated over `idx`; SHARED_KEYS entries are shared across samples (first cached copy)."""
+    x = torch.cat([inputs[i] for i in idx], dim=0)
+    sel = {}
+    for key, val in others.items():
+        if "positional_inputs" in key:
+            continue
+        if key in SHARED_KEYS:
+            if isinstance(val, list) and len(val) >= 1:
+                j = int(idx[0]) if (len(idx) == 1 and len(val) > 1) else 0
+                sel[key] = val[j] if j < len(val) else val[0]
+            else:
+                sel[key] = val
+        elif isinstance(val, list):
+            vals = [val[i] for i in idx]
+            sel[key] = vals[0] if len(vals) == 1 else torch.cat(vals, dim=0)
+        elif isinstance(val, torch.Tensor):
+            sel[key] = torch.index_select(val, 0, torch.tensor(list(idx)))
+        else:
+            sel[key] = val
+    return x, sel
+
+
+def block_forward(block, hidden, others: dict, amp=True, amp_dtype=torch.bfloat16):
+    kw = dict(others)
+    if amp:
+        with torch.autocast(device_type="cpu", dtype=amp_dtype):
+            out = block(hidden, **kw)
+    else:
+        out = block(hidden, **kw)
+    return out[0] if isinstance(out, (tuple, list)) else out
+
+
+def masked_mse(pred, ref, mask):
+    """quantizer.py:142-156 -- MSELoss('mean') over ALL elements; masked tokens contribute zeros."""
+    if mask is not None:
+        return F.mse_loss((pred * mask).to(torch.float32), (ref * mask).to(torch.float32))
+    return F.mse_loss(pred.to(torch.float32), ref.to(torch.float32))
+
+
+@dataclass
+class TuneResult:
+    losses: list = field(default_factory=list)     # total_loss per iteration (loss.item()/num_elm)
+    best_iter: int = 0
+    best_loss: float = float("inf")
+    best_params: dict = field(default_factory=dict)
+    batches: list = field(default_factory=list)
+
+
+def tune_block(block, inputs, others, fp_outputs, scheme_of, iters=200, batch_size=8, lr=None, minmax_lr=None,
+               token_masks=None, enable_minmax_tuning=True, nv_global_scales=None, amp=True,
+               not_use_best_mse=False, sampler=None) -> TuneResult:
+    """quantize_block: `inputs`/`fp_outputs` are per-sample lists of [1,S,H]; `token_masks` per-sample [1,S]
+    long tensors (1 = valid) or None.  Mutates `block` in place (qdq weights + scale/zp attributes)."""
+    nsamples = len(inputs)
+    wrapped = wrap_block(block, scheme_of, nv_global_scales)
+    res = TuneResult()
+    if not wrapped:
+        return res
+
+    def lr_for(bits):
+        if lr is not None:
+            return lr
+        return 2.0 / iters if (iters >= 1000 and bits <= 3) else 1.0 / iters
+
+    # one lr tensor per param group, scaled by the same LinearLR factors (quantizer.py:374-429)
+    groups = []
+    for tl in wrapped.values():
+        base = lr_for(tl.scheme.bits)
+        groups.append(([tl.value], torch.tensor(float(base))))
+        if enable_minmax_tuning:
+            mm = [tl.max_scale] if tl.scheme.data_type != "int" else [tl.min_scale, tl.max_scale]
+            groups.append((mm, torch.tensor(float(minmax_lr if minmax_lr is not None else base))))
+    if not enable_minmax_tuning:
+        for tl in wrapped.values():
+            tl.min_scale.requires_grad_(False)
+            tl.max_scale.requires_grad_(False)
+
+    gbs = min(nsamples, batch_size)
+    sampler = sampler if sampler is not None else IndexSampler(nsamples, gbs)
+    best_loss = torch.finfo(torch.float).max
+    for it in range(iters):
+        idx = sampler.next_batch()
+        res.batches.append(list(idx))
+        num_elm = 1
+        mask = None
+        if token_masks:
+            num_elm = sum(int(torch.count_nonzero(token_masks[i]).item()) for i in idx)
+            mask = torch.cat([token_masks[i] for i in idx], dim=0).unsqueeze(-1)
+        ref = torch.cat([fp_outputs[i] for i in idx], dim=0)
+        x, sel = select_batch(inputs, others, idx)
+        pred = block_forward(block, x, sel, amp)
+        loss = masked_mse(pred, ref, mask)
+        num_elm = 1 if num_elm <= 0 else num_elm
+        total = loss.item() / num_elm
+        (loss * 1000).backward()
+        res.losses.append(total)
+        if total < best_loss:
+            best_loss = total
+            if not not_use_best_mse:
+                res.best_params = {n: {k: p.data.clone() for k, p in tl.params.items()} for n, tl in wrapped.items()}
+                res.best_iter = it
+        if not_use_best_mse and it == iters - 1:
+            res.best_params = {n: {k: p.data.clone() for k, p in tl.params.items()} for n, tl in wrapped.items()}
+            res.best_iter = it
+        # sign-SGD step + zero_grad + LinearLR(1 -> 0 over iters)
+        with torch.no_grad():
+            for params, lr_t in groups:
+                for p in params:
+                    if p.grad is not None:
+                        p.add_(torch.sign(p.grad), alpha=-lr_t.item())
+                        p.grad = None
+        # LinearLR(start 1 -> end 0 over `iters`), chainable form: lr *= 1 - 1/(iters - it), in the lr tensor's fp32
+        for _, lr_t in groups:
+            lr_t.mul_(1.0 + (0.0 - 1.0) / (iters * 1.0 + it * (0.0 - 1.0)))
+    res.best_loss = best_loss
+    with torch.no_grad():
+        unwrap_block(block, wrapped, res.best_params)
+    return res

@@ -1,0 +1,182 @@
+"""Pins the CPU oracle (oracle/) against fixtures produced by the UNMODIFIED reference
+(oracle/gen_golden.py -> tests/golden/*.pt).  Everything here is bit-exact: the oracle restates the
+reference with the same torch-CPU ops in the same order."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pack as P
+from oracle import qdq as Q
+from oracle import signround as S
+
+
+def _same(a, b):
+    """bit-equality that also accepts NaN==NaN (the reference yields NaN d(max_scale) for an all-zero
+    NVFP4 group: 0 * inf in its autograd graph)."""
+    return a.shape == b.shape and torch.equal(torch.isnan(a), torch.isnan(b)) and \
+        torch.equal(torch.nan_to_num(a, nan=0.0), torch.nan_to_num(b, nan=0.0))
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _run_qdq(name, rec):
+    kw = rec["kw"]
+    w = rec["w"]
+    v = rec["v"].clone().requires_grad_(True)
+    mn = rec["min_scale"].clone().requires_grad_(True)
+    mx = rec["max_scale"].clone().requires_grad_(True)
+    if name.startswith("int_sym"):
+        wmin, wmax = Q.group_minmax(w, kw["group_size"])
+        out = Q.int_sym(w, kw["bits"], kw["group_size"], v, mn, mx, wmin, wmax)
+    elif name.startswith("int_asym"):
+        wmin, wmax = Q.group_minmax(w, kw["group_size"])
+        out = Q.int_asym(w, kw["bits"], kw["group_size"], v, mn, mx, wmin, wmax)
+    elif name.startswith("mx"):
+        out = Q.mx_fp4(w, kw["group_size"], v, mx)
+    else:
+        out = Q.nv_fp4(w, kw["group_size"], v, rec["global_scale"], mx)
+    wq, scale, zp = out
+    (wq.to(torch.float32) * rec["gq"]).sum().backward()
+    return wq.detach(), scale.detach(), zp, v.grad, mn.grad, mx.grad
+
+
+def test_qdq_matches_reference_bit_exact(golden_dir):
+    gold = _load(golden_dir, "qdq.pt")
+    n = 0
+    for key, rec in gold.items():
+        if key.startswith("rtn"):
+            continue
+        name = key.split("/")[0]
+        wq, scale, zp, dv, dmn, dmx = _run_qdq(name, rec)
+        assert torch.equal(wq, rec["wq"]), key
+        assert torch.equal(scale.float(), rec["scale"].float()), key
+        if isinstance(rec["zp"], torch.Tensor):
+            assert torch.equal(zp.detach(), rec["zp"]), key
+        else:
+            assert zp == rec["zp"], key
+        assert _same(dv, rec["dv"]), key
+        if rec["dmax"] is not None:
+            assert _same(dmx, rec["dmax"]), key
+        if rec["dmin"] is not None:
+            assert _same(dmn, rec["dmin"]), key
+        else:
+            assert dmn is None, key
+        n += 1
+    assert n >= 18
+
+
+def test_rtn_matches_reference(golden_dir):
+    rec = _load(golden_dir, "qdq.pt")["rtn_int_sym_w4g128"]
+    wq, scale, zp = Q.rtn_int_sym(rec["w"].clone(), 4, 128)
+    assert torch.equal(wq, rec["wq"]) and torch.equal(scale, rec["scale"]) and zp == rec["zp"]
+
+
+def test_cast_to_fp4_known_answers():
+    # reference table: test/unit/test_cpu/data_type/test_nvfp.py:75-80 and data_type/nvfp.py:440-447
+    x = torch.tensor([0.0, 0.24, 0.25, 0.26, 0.75, 1.25, 1.75, 2.5, 3.5, 5.0, 7.0, -0.75, -2.5, -5.0])
+    want = torch.tensor([0.0, 0.0, 0.0, 0.5, 1.0, 1.0, 2.0, 2.0, 4.0, 4.0, 6.0, -1.0, -2.0, -4.0])
+    assert torch.equal(Q.cast_to_fp4(x), want)
+
+
+def test_nv_global_scale_formula():
+    # calculate_gparam = 448*6/amax (test_nvfp.py:174-179)
+    w = torch.tensor([[0.5, -2.0, 1.0]])
+    assert float(Q.nv_global_scale(w)) == pytest.approx(448.0 * 6.0 / 2.0)
+    assert float(Q.nv_global_scale(0.0)) == 0.0
+
+
+def test_fp4_nibble_known_answers():
+    # test/unit/test_cpu/export/test_qlinear_fp_helpers.py:174-221
+    assert P._two_per_byte(P.fp4_nibbles(torch.tensor([[6.0, 6.0]])))[0, 0] == 0x77
+    assert P._two_per_byte(P.fp4_nibbles(torch.tensor([[-6.0, -6.0]])))[0, 0] == 0xFF
+    assert P._two_per_byte(P.fp4_nibbles(torch.tensor([[0.5, 0.5]])))[0, 0] == 0x11
+    assert P._two_per_byte(P.fp4_nibbles(torch.tensor([[0.0, -0.0]])))[0, 0] == 0x80
+
+
+def test_pack_matches_reference_bit_exact(golden_dir):
+    gold = _load(golden_dir, "pack.pt")
+    for key, rec in gold.items():
+        if key.startswith("int"):
+            out = P.pack_int(rec["wq"], rec["scale"], rec["zp"], rec["bits"], rec["group_size"],
+                             zp_minus_one=key.endswith("gptq_zp"))
+            assert np.array_equal(out["qweight"], rec["qweight"].numpy()), key
+            assert np.array_equal(out["qzeros"], rec["qzeros"].numpy()), key
+            assert np.array_equal(out["scales"], rec["scales"].numpy()), key
+            if "g_idx" in rec:
+                assert np.array_equal(out["g_idx"], rec["g_idx"].numpy()), key
+        elif key == "nv_fp4":
+            out = P.pack_nvfp4(rec["wq"], rec["scale"], rec["global_scale"])
+            assert np.array_equal(out["weight_packed"], rec["weight_packed"].numpy())
+            assert np.array_equal(out["weight_scale"], rec["weight_scale"].numpy())
+            assert np.array_equal(out["weight_global_scale"], rec["weight_global_scale"].numpy())
+        else:
+            out = P.pack_mxfp4(rec["wq"], rec["scale"])
+            assert np.array_equal(out["weight_packed"], rec["weight_packed"].numpy())
+            assert np.array_equal(out["weight_scale"], rec["weight_scale"].numpy())
+
+
+def test_pack_unpack_roundtrip():
+    codes = np.random.default_rng(0).integers(0, 16, size=(64, 256)).astype(np.int32)
+    assert np.array_equal(P.unpack_int(P._pack_rows_pow2(codes, 4).T.copy(), 4), codes)
+
+
+SCHEMES = {
+    "w4a16_sym_g32": S.LayerScheme(4, 32, True, "int"),
+    "w2a16_asym_g32": S.LayerScheme(2, 32, False, "int"),
+    "nvfp4": S.LayerScheme(4, 16, True, "nv_fp"),
+    "mxfp4": S.LayerScheme(4, 32, True, "mx_fp"),
+}
+
+
+def _tiny_block(state):
+    from transformers import LlamaConfig
+    from transformers.models.llama.modeling_llama import LlamaDecoderLayer
+
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, vocab_size=128, max_position_embeddings=64, rms_norm_eps=1e-5,
+                      rope_theta=10000.0, tie_word_embeddings=False)
+    cfg._attn_implementation = "sdpa"
+    blk = LlamaDecoderLayer(cfg, 0).to(torch.bfloat16).eval()
+    blk.load_state_dict(state)
+    return blk
+
+
+@pytest.mark.parametrize("tag", list(SCHEMES))
+def test_tune_block_matches_reference_bit_exact(golden_dir, tag):
+    rec = _load(golden_dir, f"block_{tag}.pt")
+    sc = SCHEMES[tag]
+    for b in rec["blocks"]:
+        blk = _tiny_block(b["block_state"])
+        masks = [(ids != -100).to(torch.long) for ids in b["input_ids"]]
+        res = S.tune_block(blk, b["inputs"], b["others"], b["fp_outputs"], lambda n, m: sc, iters=rec["iters"],
+                           batch_size=rec["batch_size"], token_masks=masks, nv_global_scales=b["nv_gs"] or None,
+                           sampler=S.ReplaySampler(b["batches"]))
+        # the fixture logs the raw mean loss (before /num_elm); compare via the same normalisation
+        assert len(res.losses) == len(b["losses"])
+        nvalid = [sum(int(masks[i].sum()) for i in batch) for batch in b["batches"]]
+        got = [l * n for l, n in zip(res.losses, nvalid)]
+        assert got == pytest.approx(b["losses"], rel=1e-6)
+        for name, lay in b["layers"].items():
+            mod = blk.get_submodule(name)
+            assert torch.equal(mod.weight.data, lay["weight"]), (tag, name)
+            assert torch.equal(mod.scale.float().reshape(-1), lay["scale"].float().reshape(-1)), (tag, name)
+            if isinstance(lay["zp"], torch.Tensor):
+                assert torch.equal(mod.zp.reshape(-1), lay["zp"].reshape(-1)), (tag, name)
+
+
+def test_index_sampler_is_python_random():
+    import random
+
+    random.seed(42)
+    s = S.IndexSampler(8, 4)
+    got = [s.next_batch() for _ in range(4)]
+    random.seed(42)
+    idx = list(range(8))
+    random.shuffle(idx)
+    assert got[0] == idx[:4] and got[1] == idx[4:]
+    random.shuffle(idx)
+    assert got[2] == idx[:4]
