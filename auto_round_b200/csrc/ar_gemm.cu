@@ -1,0 +1,616 @@
+// bf16 GEMMs of the fake-quant linear on 5th-gen tensor cores (tcgen05) for sm_100a.
+//
+//   D[M,N] = A[M,K] · B[N,K]ᵀ ,  fp32 accumulate in TMEM, operands staged by TMA into 128B-swizzled smem.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   (one elected lane; 4-stage ring, mbarrier full/empty)
+//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma 128 x BN x 16; owns TMEM alloc/free)
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b: thread <-> accumulator row; double-buffered accumulator
+//                               so the epilogue of tile i overlaps the main loop of tile i+1)
+// Each operand may be K-major (reduction dim contiguous) or MN-major (row dim contiguous), which covers the
+// three GEMMs of a linear without any transposed copies:
+//   forward   Y  = X  · Wqᵀ      A = X  [T,K]  K-major      B = Wq [N,K]  K-major
+//   grad-in   dX = dY · Wq       A = dY [T,N]  K-major      B = Wq [N,K]  as [K_out, N_red]: MN-major
+//   grad-w    dW = dYᵀ· X        A = dY [T,N]  as [N_out, T_red]: MN-major   B = X [T,K] as [K_out, T_red]: MN-major
+// Epilogues:
+//   EPI_STORE  fp32 -> (+bias) -> bf16 -> swizzled smem -> TMA store
+//   EPI_DW     fp32 dWq tile -> fake-quant backward in registers -> dV (fp32), d min/max_scale per group; the
+//              dWq matrix itself is never written (auto_round: autograd through wrapper.py:273-290)
+// FLOPs per launch = 2*M*N*K; roofline = dense bf16 tensor peak (MEASURED_PEAKS.json: bf16_tflops).
+#include <cuda.h>
+
+#include <mutex>
+
+#include "ar_qdq_math.cuh"
+
+namespace ar {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;           // 64 bf16 = 128 B = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kNumThreads = 192;      // 6 warps
+constexpr int kEpiThreads = 128;
+constexpr int kEpiFirstWarp = 2;
+
+enum { EPI_STORE = 0, EPI_DW = 1 };
+
+// ------------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xFFFFFFFF;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread t of the warp gets row (lane_base + t), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B:
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------- kernel params
+struct DwParams {                 // EPI_DW: fake-quant backward inputs/outputs
+  const uint16_t* w;              // bf16 [N,K]
+  const float* v;                 // fp32 [N,K] or null
+  const float* mn;                // [G] or null
+  const float* mx;                // [G] or null
+  const uint16_t* wmin;           // bf16 [G] (int types)
+  const uint16_t* wmax;
+  const float* gscale;            // nv
+  float* dv;                      // fp32 [N,K]
+  float* dmin;                    // [G] or null
+  float* dmax;                    // [G] or null
+  int bits;
+  float thr;
+  int accumulate;
+};
+
+struct GemmParams {
+  int m, n, k;                    // logical problem: D[m,n] = A[m,k] B[n,k]^T
+  int m_tiles, n_tiles;
+  const uint16_t* bias;           // EPI_STORE, optional [n]
+  DwParams dw;
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;       // 16 KB
+  static constexpr int kBBytes = BN * BLOCK_K * 2;            // 32 KB @ BN=256
+  static constexpr int kCBytes = BLOCK_M * 64 * 2;            // one 128 x 64 bf16 store box
+  static constexpr int kAOff = 0;
+  static constexpr int kBOff = kStages * kABytes;
+  static constexpr int kCOff = kBOff + kStages * kBBytes;
+  static constexpr int kBarOff = kCOff + 2 * kCBytes;
+  static constexpr int kTotal = kBarOff + 256;
+};
+
+// tile order: groups of 8 M-tiles sweep all N-tiles, so the ~148 concurrent CTAs share A/B tiles in L2
+__device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int& mt, int& nt) {
+  constexpr int GM = 8;
+  const int per_group = GM * n_tiles;
+  const int grp = t / per_group;
+  const int first = grp * GM;
+  const int gm = min(GM, m_tiles - first);
+  const int in = t - grp * per_group;
+  mt = first + in % gm;
+  nt = in / gm;
+}
+
+// ------------------------------------------------------------------------------------- dW fused epilogue
+// Thread owns accumulator row `row` (= output feature n) and walks its BN columns (= input features k) in chunks of 32.
+template <class Ctx, int G, bool IS_FP4, int BN>
+__device__ __forceinline__ void epilogue_dw(const GemmParams& p, uint32_t tmem_acc, int row, int col0) {
+  const DwParams& d = p.dw;
+  const int N = p.m, K = p.n;                     // GEMM "m" is the layer's N (out features), GEMM "n" its K
+  const bool row_ok = row < N;
+  const int gpr = K / G;
+  Ctx ctx;
+  ctx.init(d.bits);
+  GroupIn gi;
+  gi.thr = d.thr;
+  gi.gscale = (IS_FP4 && d.gscale) ? *d.gscale : 0.f;
+  GroupAcc acc;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    const int k0 = col0 + c * 32;
+    uint32_t r[32];
+    tmem_ld32(tmem_acc + (uint32_t)(c * 32), r);   // warp-collective: every lane executes it
+    tmem_ld_wait();
+    if (!row_ok || k0 >= K) continue;
+    const int64_t off = (int64_t)row * K + k0;
+    float w[32], v[32];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const U4 q = reinterpret_cast<const U4*>(d.w + off)[j];
+      const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        w[j * 8 + 2 * i] = bf16_bits_to_f32((uint16_t)(u[i] & 0xffffu));
+        w[j * 8 + 2 * i + 1] = bf16_bits_to_f32((uint16_t)(u[i] >> 16));
+      }
+    }
+    if (d.v) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 q = reinterpret_cast<const float4*>(d.v + off)[j];
+        v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    }
+    float out[32];
+    constexpr int SUB = (G < 32) ? G : 32;         // elements of one group inside this chunk
+#pragma unroll
+    for (int s = 0; s < 32 / SUB; ++s) {
+      const int kk = k0 + s * SUB;
+      const int64_t gidx = (int64_t)row * gpr + kk / G;
+      if ((kk % G) == 0) {                         // group starts here: build its context
+        gi.mn = d.mn ? d.mn[gidx] : 1.f;
+        gi.mx = d.mx ? d.mx[gidx] : 1.f;
+        if (IS_FP4) {
+          float am = 0.f;
+#pragma unroll
+          for (int i = 0; i < SUB; ++i) am = fmaxf(am, fabsf(w[s * SUB + i]));
+          gi.wmax = am; gi.wmin = 0.f;             // G <= 32 for fp4: the whole group is in registers
+        } else {
+          gi.wmin = bf16_bits_to_f32(d.wmin[gidx]);
+          gi.wmax = bf16_bits_to_f32(d.wmax[gidx]);
+        }
+        ctx.setup(gi);
+        acc = GroupAcc();
+      }
+#pragma unroll
+      for (int i = 0; i < SUB; ++i) ctx.bwd(w[s * SUB + i], v[s * SUB + i], __uint_as_float(r[s * SUB + i]), out[s * SUB + i], acc);
+      if (((kk + SUB) % G) == 0) {                 // group complete
+        float gmn, gmx;
+        ctx.finish(acc, gi, gmn, gmx);
+        if (d.dmax) d.dmax[gidx] = d.accumulate ? d.dmax[gidx] + gmx : gmx;
+        if (d.dmin) d.dmin[gidx] = d.accumulate ? d.dmin[gidx] + gmn : gmn;
+      }
+    }
+    float* o = d.dv + off;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 q = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+      if (d.accumulate) {
+        const float4 old = reinterpret_cast<const float4*>(o)[j];
+        q.x += old.x; q.y += old.y; q.z += old.z; q.w += old.w;
+      }
+      reinterpret_cast<float4*>(o)[j] = q;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- the kernel
+template <bool A_MN, bool B_MN, int BN, int EPI, class Ctx, int G, bool IS_FP4>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+            const __grid_constant__ CUtensorMap map_d, const GemmParams p) {
+  using L = SmemLayout<BN>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* full = bars;                       // [kStages]
+  uint64_t* empty = bars + kStages;            // [kStages]
+  uint64_t* tfull = bars + 2 * kStages;        // [2]
+  uint64_t* tempty = bars + 2 * kStages + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_kb = (p.k + BLOCK_K - 1) / BLOCK_K;
+  constexpr uint32_t kTmemCols = 2 * BN;       // two accumulator stages (256 or 512: powers of two)
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+    if (EPI == EPI_STORE) prefetch_tmap(&map_d);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiThreads); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int mt, nt;
+        tile_coords(t, p.m_tiles, p.n_tiles, mt, nt);
+        const int m0 = mt * BLOCK_M, n0 = nt * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_expect_tx(&full[s], L::kABytes + L::kBBytes);
+          uint8_t* sa = smem + L::kAOff + s * L::kABytes;
+          uint8_t* sb = smem + L::kBOff + s * L::kBBytes;
+          const int k0 = kb * BLOCK_K;
+          if (!A_MN) {
+            tma_load_2d(sa, &map_a, &full[s], k0, m0);                       // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i)                           // box {64 m, 64 k} per 64-wide atom
+              tma_load_2d(sa + i * (64 * BLOCK_K * 2), &map_a, &full[s], m0 + i * 64, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &map_b, &full[s], k0, n0);                       // box {64 k, BN n}
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(sb + i * (64 * BLOCK_K * 2), &map_b, &full[s], n0 + i * 64, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BLOCK_M, BN);
+    // K-major:  SBO = 8 rows * 128 B (next 8-row core-matrix group), LBO unused;  K step (16 elem) = +32 B
+    // MN-major: SBO = 8 k-rows * 128 B, LBO = 64 k-rows * 128 B (next 64-wide MN atom); K step (16 rows) = +2048 B
+    constexpr uint32_t a_lbo = A_MN ? (BLOCK_K * 128) : 0, b_lbo = B_MN ? (BLOCK_K * 128) : 0;
+    constexpr uint32_t a_kstep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2), b_kstep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
+    uint32_t it = 0, local_tile = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local_tile) {
+      const uint32_t as = local_tile & 1u, aph = (local_tile >> 1) & 1u;
+      mbar_wait(&tempty[as], aph ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + L::kAOff + s * L::kABytes);
+          const uint32_t sb = smem_u32(smem + L::kBOff + s * L::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);                          // frees the smem stage when these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tfull[as]);   // accumulator complete -> epilogue
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================================================== epilogue warps
+    const int q = warp & 3;                                // TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
+    const int epi_tid = threadIdx.x - kEpiFirstWarp * 32;
+    uint32_t local_tile = 0, store_idx = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local_tile) {
+      int mt, nt;
+      tile_coords(t, p.m_tiles, p.n_tiles, mt, nt);
+      const int m0 = mt * BLOCK_M, n0 = nt * BN;
+      const uint32_t as = local_tile & 1u, aph = (local_tile >> 1) & 1u;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+      if constexpr (EPI == EPI_DW) {
+        epilogue_dw<Ctx, G, IS_FP4, BN>(p, tmem_acc, m0 + row_in_tile, n0);
+        tc_fence_before();
+        mbar_arrive(&tempty[as]);
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c, ++store_idx) {
+          uint8_t* sc = smem + L::kCOff + (store_idx & 1u) * L::kCBytes;
+          // the store issued two chunks ago must have finished READING this smem buffer
+          if (epi_tid == 0) tma_store_wait_read<1>();
+          epi_bar_sync();
+          uint32_t r0[32], r1[32];
+          tmem_ld32(tmem_acc + (uint32_t)(c * 64), r0);
+          tmem_ld32(tmem_acc + (uint32_t)(c * 64 + 32), r1);
+          tmem_ld_wait();
+          if (c == BN / 64 - 1) {                           // accumulator fully read: hand TMEM back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&tempty[as]);
+          }
+          const int nbase = n0 + c * 64;
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float x0 = __uint_as_float(r0[2 * i]), x1 = __uint_as_float(r0[2 * i + 1]);
+            float y0 = __uint_as_float(r1[2 * i]), y1 = __uint_as_float(r1[2 * i + 1]);
+            if (p.bias) {
+              // F.linear under autocast: bf16 GEMM result (+bias in fp32 inside the fused epilogue)
+              const int n_a = nbase + 2 * i, n_b = nbase + 32 + 2 * i;
+              if (n_a < p.n) x0 += bf16_bits_to_f32(p.bias[n_a]);
+              if (n_a + 1 < p.n) x1 += bf16_bits_to_f32(p.bias[n_a + 1]);
+              if (n_b < p.n) y0 += bf16_bits_to_f32(p.bias[n_b]);
+              if (n_b + 1 < p.n) y1 += bf16_bits_to_f32(p.bias[n_b + 1]);
+            }
+            pk[i] = (uint32_t)f32_to_bf16_bits(x0) | ((uint32_t)f32_to_bf16_bits(x1) << 16);
+            pk[16 + i] = (uint32_t)f32_to_bf16_bits(y0) | ((uint32_t)f32_to_bf16_bits(y1) << 16);
+          }
+          // 128B-swizzled staging tile: row r -> 128 B, 16-byte chunk j stored at (j ^ (r & 7))
+          uint8_t* rowp = sc + row_in_tile * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int pj = j ^ (row_in_tile & 7);
+            *reinterpret_cast<U4*>(rowp + pj * 16) = U4{pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]};
+          }
+          fence_proxy_async();
+          epi_bar_sync();
+          if (epi_tid == 0) {
+            tma_store_2d(&map_d, sc, nbase, m0);             // box {64 n, 128 m}; out-of-range rows/cols are clipped
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (EPI == EPI_STORE && epi_tid == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)f;
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: dim0 = contiguous dimension.  box = {box0, box1}, 128B swizzle (box0 * 2 B == 128 B).
+static int make_map(CUtensorMap* map, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride1_elems, uint32_t box0,
+                    uint32_t box1) {
+  PFN_encodeTiled enc = get_encode();
+  AR_REQUIRE(enc != nullptr, AR_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  AR_REQUIRE(((uintptr_t)ptr & 15u) == 0, AR_E_BADARG, "TMA operand must be 16-byte aligned");
+  AR_REQUIRE((stride1_elems * 2) % 16 == 0, AR_E_BADARG, "TMA leading dimension must be a multiple of 8 elements (got %llu)",
+             (unsigned long long)stride1_elems);
+  cuuint64_t gdim[2] = {dim0, dim1};
+  cuuint64_t gstr[1] = {stride1_elems * 2};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AR_REQUIRE(r == CUDA_SUCCESS, AR_E_DRIVER, "cuTensorMapEncodeTiled failed (%d) dims=%llu,%llu stride=%llu box=%u,%u", (int)r,
+             (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)stride1_elems, box0, box1);
+  return AR_OK;
+}
+
+static int check_device() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    ok = (major == 10) ? 1 : 0;
+  }
+  AR_REQUIRE(ok == 1, AR_E_NOTSM100, "tcgen05 kernels need an sm_100 device");
+  return AR_OK;
+}
+
+template <bool A_MN, bool B_MN, int BN, int EPI, class Ctx, int G, bool IS_FP4>
+static int launch(const void* a, const void* b, void* d, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
+                  const GemmParams& base, cudaStream_t st) {
+  using L = SmemLayout<BN>;
+  auto kern = gemm_kernel<A_MN, B_MN, BN, EPI, Ctx, G, IS_FP4>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    AR_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(smem=%d): %s", L::kTotal, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  CUtensorMap ma, mb, md;
+  int rc;
+  if (!A_MN) rc = make_map(&ma, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, 64, BLOCK_M);   // stored [m, k]
+  else rc = make_map(&ma, a, (uint64_t)m, (uint64_t)k, (uint64_t)lda, 64, BLOCK_K);          // stored [k, m]
+  if (rc) return rc;
+  if (!B_MN) rc = make_map(&mb, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, 64, BN);
+  else rc = make_map(&mb, b, (uint64_t)n, (uint64_t)k, (uint64_t)ldb, 64, BLOCK_K);
+  if (rc) return rc;
+  if (EPI == EPI_STORE) {
+    rc = make_map(&md, d, (uint64_t)n, (uint64_t)m, (uint64_t)ldd, 64, BLOCK_M);
+    if (rc) return rc;
+  } else {
+    md = ma;
+  }
+  GemmParams p = base;
+  p.m = m; p.n = n; p.k = k;
+  p.m_tiles = (m + BLOCK_M - 1) / BLOCK_M;
+  p.n_tiles = (n + BN - 1) / BN;
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, kNumThreads, L::kTotal, st>>>(ma, mb, md, p);
+  AR_CHECK_LAUNCH();
+  return AR_OK;
+}
+
+struct NoCtx {};
+
+}  // namespace ar
+
+using namespace ar;
+
+extern "C" int ar_gemm_bf16(const void* a, const void* b, void* d, int m, int n, int k, int a_mn, int b_mn, int64_t lda,
+                            int64_t ldb, int64_t ldd, const void* bias, void* stream) {
+  AR_REQUIRE(a && b && d && m > 0 && n > 0 && k > 0, AR_E_BADARG, "bad gemm args m=%d n=%d k=%d", m, n, k);
+  if (int rc = check_device()) return rc;
+  GemmParams p{};
+  p.bias = (const uint16_t*)bias;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!a_mn && !b_mn) return launch<false, false, 256, EPI_STORE, NoCtx, 32, false>(a, b, d, m, n, k, lda, ldb, ldd, p, st);
+  if (!a_mn && b_mn) return launch<false, true, 256, EPI_STORE, NoCtx, 32, false>(a, b, d, m, n, k, lda, ldb, ldd, p, st);
+  if (a_mn && !b_mn) return launch<true, false, 256, EPI_STORE, NoCtx, 32, false>(a, b, d, m, n, k, lda, ldb, ldd, p, st);
+  return launch<true, true, 256, EPI_STORE, NoCtx, 32, false>(a, b, d, m, n, k, lda, ldb, ldd, p, st);
+}
+
+extern "C" int ar_fq_linear_fwd(const ar_qspec* q, const void* x, int64_t t, const void* w, const float* v, const float* mn,
+                                const float* mx, const void* wmin, const void* wmax, const float* gscale, const void* bias,
+                                void* wq_scratch, void* y, void* stream) {
+  AR_REQUIRE(q && x && w && wq_scratch && y && t > 0, AR_E_BADARG, "null pointer");
+  if (int rc = ar_qdq_fwd(q, w, v, mn, mx, wmin, wmax, gscale, wq_scratch, nullptr, nullptr, stream)) return rc;
+  return ar_gemm_bf16(x, wq_scratch, y, (int)t, q->n, q->k, 0, 0, q->k, q->k, q->n, bias, stream);
+}
+
+extern "C" int ar_fq_linear_bwd_dx(const ar_qspec* q, const void* dy, int64_t t, const void* wq, void* dx, void* stream) {
+  AR_REQUIRE(q && dy && wq && dx && t > 0, AR_E_BADARG, "null pointer");
+  // dX[T,K] = dY[T,N] · Wq[N,K]:  A = dY (K-major over N), B = Wq viewed as [K_out, N_red] -> MN-major
+  return ar_gemm_bf16(dy, wq, dx, (int)t, q->k, q->n, 0, 1, q->n, q->k, q->k, nullptr, stream);
+}
+
+extern "C" int ar_fq_linear_bwd_dw(const ar_qspec* q, const void* dy, const void* x, int64_t t, const void* w, const float* v,
+                                   const float* mn, const float* mx, const void* wmin, const void* wmax, const float* gscale,
+                                   float* dv, float* dmin, float* dmax, int accumulate, void* stream) {
+  AR_REQUIRE(q && dy && x && w && dv && t > 0, AR_E_BADARG, "null pointer");
+  if (int rc = check_device()) return rc;
+  const int N = q->n, K = q->k, g = q->group_size;
+  AR_REQUIRE(K % g == 0 && K % 32 == 0, AR_E_UNSUPPORTED, "fused dW epilogue needs K %% group_size == 0 and K %% 32 == 0");
+  const bool is_int = (q->dtype == AR_DT_INT_SYM || q->dtype == AR_DT_INT_ASYM);
+  AR_REQUIRE(!is_int || (wmin && wmax), AR_E_BADARG, "int types need wmin/wmax (ar_group_minmax)");
+  AR_REQUIRE(q->dtype != AR_DT_NV_FP4 || gscale, AR_E_BADARG, "nv_fp4 needs gscale");
+  GemmParams p{};
+  p.dw = DwParams{(const uint16_t*)w, v, mn, mx, (const uint16_t*)wmin, (const uint16_t*)wmax, gscale, dv, dmin, dmax,
+                  q->bits, q->q_scale_thresh, accumulate};
+  cudaStream_t st = (cudaStream_t)stream;
+  // D[N_out, K_out] = sum_t dY[t,n] X[t,k]:  A = dY stored [T,N] (MN-major), B = X stored [T,K] (MN-major)
+#define AR_DW(CTX, GG, FP4) \
+  return launch<true, true, 256, EPI_DW, CTX, GG, FP4>(dy, x, nullptr, N, K, (int)t, (int64_t)N, (int64_t)K, 0, p, st)
+  if (q->dtype == AR_DT_INT_SYM) {
+    if (g == 32) AR_DW(IntSym, 32, false);
+    if (g == 64) AR_DW(IntSym, 64, false);
+    if (g == 128) AR_DW(IntSym, 128, false);
+  } else if (q->dtype == AR_DT_INT_ASYM) {
+    if (g == 32) AR_DW(IntAsym, 32, false);
+    if (g == 64) AR_DW(IntAsym, 64, false);
+    if (g == 128) AR_DW(IntAsym, 128, false);
+  } else if (q->dtype == AR_DT_MX_FP4) {
+    if (g == 32) AR_DW(MxFp4, 32, true);
+  } else if (q->dtype == AR_DT_NV_FP4) {
+    if (g == 16) AR_DW(NvFp4, 16, true);
+  }
+#undef AR_DW
+  AR_REQUIRE(false, AR_E_UNSUPPORTED, "fused dW epilogue: dtype %d with group_size %d not built", q->dtype, g);
+}

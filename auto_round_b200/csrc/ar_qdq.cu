@@ -1,0 +1,391 @@
+// Standalone fake-quant kernels: forward (Wq, scale, zp), backward (dV, d min/max_scale), group min/max,
+// tensor amax.  HBM-bound elementwise work: 8 consecutive K-elements per lane (16 B bf16 loads, 2x16 B fp32
+// loads), a quantisation group spans g/8 adjacent lanes of one warp, group reductions are shuffles.
+//   algorithmic bytes / weight:  fwd 2 (W) + 4 (V) + 2 (Wq) = 8 B;  bwd 2 + 4 + 4 (Gq) + 4 (dV) = 14 B
+#include "ar_qdq_math.cuh"
+
+namespace ar {
+
+constexpr int kThreads = 256;
+
+struct QArgs {
+  const uint16_t* w;
+  const float* v;
+  const float* mn;
+  const float* mx;
+  const uint16_t* wmin;
+  const uint16_t* wmax;
+  const float* gscale;
+  int n, k, kpad, bits;
+  float thr;
+};
+
+template <int LPG>
+__device__ __forceinline__ float group_max(float x) {
+#pragma unroll
+  for (int o = LPG / 2; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+  return x;
+}
+template <int LPG>
+__device__ __forceinline__ float group_min(float x) {
+#pragma unroll
+  for (int o = LPG / 2; o > 0; o >>= 1) x = fminf(x, __shfl_xor_sync(0xffffffffu, x, o));
+  return x;
+}
+template <int LPG>
+__device__ __forceinline__ float group_sum(float x) {
+#pragma unroll
+  for (int o = LPG / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+// load 8 consecutive elements of row n starting at k0 (zero beyond K: the reference zero-pads K to a group multiple)
+__device__ __forceinline__ void load_w8(const uint16_t* w, int64_t row_off, int k0, int k, bool vec, float (&out)[8]) {
+  if (vec && k0 + 8 <= k) {
+    const U4 r = *reinterpret_cast<const U4*>(w + row_off + k0);
+    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      out[2 * i] = bf16_bits_to_f32((uint16_t)(u[i] & 0xffffu));
+      out[2 * i + 1] = bf16_bits_to_f32((uint16_t)(u[i] >> 16));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = (k0 + i < k) ? bf16_bits_to_f32(w[row_off + k0 + i]) : 0.f;
+  }
+}
+__device__ __forceinline__ void load_f8(const float* p, int64_t off, float (&out)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p + off);
+  const float4 b = *reinterpret_cast<const float4*>(p + off + 4);
+  out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+  out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+}
+
+template <class Ctx, int G, bool IS_FP4>
+__device__ __forceinline__ void make_group(const QArgs& a, int64_t gidx, const float (&w)[8], bool valid, Ctx& ctx,
+                                           GroupIn& gi) {
+  constexpr int LPG = G / 8;
+  gi.thr = a.thr;
+  ctx.init(a.bits);
+  gi.gscale = (IS_FP4 && a.gscale) ? *a.gscale : 0.f;
+  gi.mn = (valid && a.mn) ? a.mn[gidx] : 1.f;
+  gi.mx = (valid && a.mx) ? a.mx[gidx] : 1.f;
+  if (IS_FP4) {
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(w[i]));
+    gi.wmax = group_max<LPG>(m);
+    gi.wmin = 0.f;
+  } else if (a.wmin != nullptr) {
+    gi.wmin = valid ? bf16_bits_to_f32(a.wmin[gidx]) : 0.f;
+    gi.wmax = valid ? bf16_bits_to_f32(a.wmax[gidx]) : 0.f;
+  } else {
+    float lo = 0.f, hi = 0.f;   // clamp(min, max=0) / clamp(max, min=0)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { lo = fminf(lo, w[i]); hi = fmaxf(hi, w[i]); }
+    gi.wmin = group_min<LPG>(lo);
+    gi.wmax = group_max<LPG>(hi);
+  }
+  ctx.setup(gi);
+}
+
+enum ScaleKind { SCALE_F16 = 0, SCALE_BF16 = 1, SCALE_F32 = 2 };
+
+template <class Ctx, int G, bool IS_FP4, int SKIND>
+__global__ void __launch_bounds__(kThreads) qdq_fwd_kernel(QArgs a, uint16_t* wq, void* scale_out, float* zp_out) {
+  constexpr int LPG = G / 8;
+  const int cpr = a.kpad / 8;                                  // 8-element chunks per (padded) row
+  const int64_t total = (int64_t)a.n * cpr;
+  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const bool valid = c < total;
+  const int64_t cc = valid ? c : 0;
+  const int n = (int)(cc / cpr);
+  const int k0 = (int)(cc % cpr) * 8;
+  const int64_t gidx = (int64_t)n * (a.kpad / G) + k0 / G;
+  const bool vec = (a.k % 8) == 0;
+  float w[8], v[8];
+  load_w8(a.w, (int64_t)n * a.k, k0, a.k, vec, w);
+  if (a.v) load_f8(a.v, (int64_t)n * a.kpad + k0, v);
+  else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  }
+  Ctx ctx;
+  GroupIn gi;
+  make_group<Ctx, G, IS_FP4>(a, gidx, w, valid, ctx, gi);
+  if (!valid) return;
+  if (wq != nullptr) {
+    uint32_t packed[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t lo = f32_to_bf16_bits(ctx.fwd(w[2 * i], v[2 * i]));
+      const uint32_t hi = f32_to_bf16_bits(ctx.fwd(w[2 * i + 1], v[2 * i + 1]));
+      packed[i] = lo | (hi << 16);
+    }
+    if (vec && k0 + 8 <= a.k) {
+      *reinterpret_cast<U4*>(wq + (int64_t)n * a.k + k0) = U4{packed[0], packed[1], packed[2], packed[3]};
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (k0 + i < a.k) wq[(int64_t)n * a.k + k0 + i] = (uint16_t)((packed[i / 2] >> (16 * (i & 1))) & 0xffffu);
+    }
+  }
+  if ((k0 % G) == 0) {
+    if (scale_out != nullptr) {
+      const float s = ctx.scale_out();
+      if (SKIND == SCALE_F16) reinterpret_cast<__half*>(scale_out)[gidx] = __float2half_rn(s);
+      else if (SKIND == SCALE_BF16) reinterpret_cast<__nv_bfloat16*>(scale_out)[gidx] = __float2bfloat16_rn(s);
+      else reinterpret_cast<float*>(scale_out)[gidx] = s;
+    }
+    if (zp_out != nullptr) zp_out[gidx] = ctx.zp_out();
+  }
+}
+
+template <class Ctx, int G, bool IS_FP4>
+__global__ void __launch_bounds__(kThreads) qdq_bwd_kernel(QArgs a, const float* gq, float* dv, float* dmin,
+                                                           float* dmax, int accumulate) {
+  constexpr int LPG = G / 8;
+  const int cpr = a.kpad / 8;
+  const int64_t total = (int64_t)a.n * cpr;
+  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const bool valid = c < total;
+  const int64_t cc = valid ? c : 0;
+  const int n = (int)(cc / cpr);
+  const int k0 = (int)(cc % cpr) * 8;
+  const int64_t gidx = (int64_t)n * (a.kpad / G) + k0 / G;
+  const bool vec = (a.k % 8) == 0;
+  float w[8], v[8], g[8];
+  load_w8(a.w, (int64_t)n * a.k, k0, a.k, vec, w);
+  if (a.v) load_f8(a.v, (int64_t)n * a.kpad + k0, v);
+  else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  }
+  if (vec && k0 + 8 <= a.k) load_f8(gq, (int64_t)n * a.k + k0, g);
+  else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = (k0 + i < a.k) ? gq[(int64_t)n * a.k + k0 + i] : 0.f;
+  }
+  Ctx ctx;
+  GroupIn gi;
+  make_group<Ctx, G, IS_FP4>(a, gidx, w, valid, ctx, gi);
+  GroupAcc acc;
+  float d[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ctx.bwd(w[i], v[i], g[i], d[i], acc);
+  acc.a = group_sum<LPG>(acc.a);
+  acc.b = group_sum<LPG>(acc.b);
+  if (!valid) return;
+  float* o = dv + (int64_t)n * a.kpad + k0;
+  if (accumulate) {
+    float old[8];
+    load_f8(dv, (int64_t)n * a.kpad + k0, old);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] += old[i];
+  }
+  *reinterpret_cast<float4*>(o) = make_float4(d[0], d[1], d[2], d[3]);
+  *reinterpret_cast<float4*>(o + 4) = make_float4(d[4], d[5], d[6], d[7]);
+  if ((k0 % G) == 0) {
+    float gmn, gmx;
+    ctx.finish(acc, gi, gmn, gmx);
+    if (dmax) dmax[gidx] = accumulate ? dmax[gidx] + gmx : gmx;
+    if (dmin) dmin[gidx] = accumulate ? dmin[gidx] + gmn : gmn;
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads) group_minmax_kernel(QArgs a, uint16_t* omin, uint16_t* omax) {
+  constexpr int LPG = G / 8;
+  const int cpr = a.kpad / 8;
+  const int64_t total = (int64_t)a.n * cpr;
+  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const bool valid = c < total;
+  const int64_t cc = valid ? c : 0;
+  const int n = (int)(cc / cpr);
+  const int k0 = (int)(cc % cpr) * 8;
+  float w[8];
+  load_w8(a.w, (int64_t)n * a.k, k0, a.k, (a.k % 8) == 0, w);
+  float lo = 0.f, hi = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { lo = fminf(lo, w[i]); hi = fmaxf(hi, w[i]); }
+  lo = group_min<LPG>(lo);
+  hi = group_max<LPG>(hi);
+  if (valid && (k0 % G) == 0) {
+    const int64_t gidx = (int64_t)n * (a.kpad / G) + k0 / G;
+    omin[gidx] = f32_to_bf16_bits(lo);
+    omax[gidx] = f32_to_bf16_bits(hi);
+  }
+}
+
+__global__ void absmax_kernel(const uint16_t* w, int64_t numel, float* out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(bf16_bits_to_f32(w[i])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));  // m >= 0: int order == float order
+}
+__global__ void nv_gscale_kernel(const float* amax, float* gs) {
+  const float a = fabsf(*amax);
+  *gs = 448.f * 6.f * ((a == 0.f) ? 0.f : 1.f / a);   // FLOAT8_E4M3_MAX * FLOAT4_E2M1_MAX * get_reciprocal(amax)
+}
+
+// --------------------------------------------------------------------------------------------- dispatch
+static int check_spec(const ar_qspec* q) {
+  AR_REQUIRE(q != nullptr, AR_E_BADARG, "qspec is null");
+  AR_REQUIRE(q->n > 0 && q->k > 0, AR_E_BADARG, "bad shape n=%d k=%d", q->n, q->k);
+  const int g = q->group_size;
+  AR_REQUIRE(g == 16 || g == 32 || g == 64 || g == 128 || g == 256, AR_E_UNSUPPORTED,
+             "group_size %d not supported (16/32/64/128/256)", g);
+  if (q->dtype == AR_DT_INT_SYM || q->dtype == AR_DT_INT_ASYM)
+    AR_REQUIRE(q->bits == 2 || q->bits == 3 || q->bits == 4 || q->bits == 8, AR_E_UNSUPPORTED, "int bits %d", q->bits);
+  else if (q->dtype == AR_DT_MX_FP4 || q->dtype == AR_DT_NV_FP4)
+    AR_REQUIRE(q->bits == 4, AR_E_UNSUPPORTED, "fp4 requires bits=4");
+  else
+    AR_REQUIRE(false, AR_E_BADARG, "unknown dtype %d", q->dtype);
+  return AR_OK;
+}
+
+static QArgs make_args(const ar_qspec* q, const void* w, const float* v, const float* mn, const float* mx,
+                       const void* wmin, const void* wmax, const float* gscale) {
+  QArgs a;
+  a.w = (const uint16_t*)w; a.v = v; a.mn = mn; a.mx = mx;
+  a.wmin = (const uint16_t*)wmin; a.wmax = (const uint16_t*)wmax; a.gscale = gscale;
+  a.n = q->n; a.k = q->k;
+  a.kpad = (q->k + q->group_size - 1) / q->group_size * q->group_size;
+  a.thr = q->q_scale_thresh;
+  a.bits = q->bits;
+  return a;
+}
+
+template <class Ctx, bool FP4, int SK>
+static void launch_fwd_g(int g, dim3 grid, cudaStream_t st, const QArgs& a, uint16_t* wq, void* so, float* zo) {
+  switch (g) {
+    case 16: qdq_fwd_kernel<Ctx, 16, FP4, SK><<<grid, kThreads, 0, st>>>(a, wq, so, zo); break;
+    case 32: qdq_fwd_kernel<Ctx, 32, FP4, SK><<<grid, kThreads, 0, st>>>(a, wq, so, zo); break;
+    case 64: qdq_fwd_kernel<Ctx, 64, FP4, SK><<<grid, kThreads, 0, st>>>(a, wq, so, zo); break;
+    case 128: qdq_fwd_kernel<Ctx, 128, FP4, SK><<<grid, kThreads, 0, st>>>(a, wq, so, zo); break;
+    default: qdq_fwd_kernel<Ctx, 256, FP4, SK><<<grid, kThreads, 0, st>>>(a, wq, so, zo); break;
+  }
+}
+template <class Ctx, bool FP4>
+static void launch_bwd_g(int g, dim3 grid, cudaStream_t st, const QArgs& a, const float* gq, float* dv, float* dmn,
+                         float* dmx, int acc) {
+  switch (g) {
+    case 16: qdq_bwd_kernel<Ctx, 16, FP4><<<grid, kThreads, 0, st>>>(a, gq, dv, dmn, dmx, acc); break;
+    case 32: qdq_bwd_kernel<Ctx, 32, FP4><<<grid, kThreads, 0, st>>>(a, gq, dv, dmn, dmx, acc); break;
+    case 64: qdq_bwd_kernel<Ctx, 64, FP4><<<grid, kThreads, 0, st>>>(a, gq, dv, dmn, dmx, acc); break;
+    case 128: qdq_bwd_kernel<Ctx, 128, FP4><<<grid, kThreads, 0, st>>>(a, gq, dv, dmn, dmx, acc); break;
+    default: qdq_bwd_kernel<Ctx, 256, FP4><<<grid, kThreads, 0, st>>>(a, gq, dv, dmn, dmx, acc); break;
+  }
+}
+
+}  // namespace ar
+
+using namespace ar;
+
+extern "C" int ar_qdq_fwd(const ar_qspec* q, const void* w, const float* v, const float* mn, const float* mx,
+                          const void* wmin, const void* wmax, const float* gscale, void* wq, void* scale_out,
+                          float* zp_out, void* stream) {
+  if (int rc = check_spec(q)) return rc;
+  AR_REQUIRE(w != nullptr, AR_E_BADARG, "w is null");
+  AR_REQUIRE((wmin == nullptr) == (wmax == nullptr), AR_E_BADARG, "wmin/wmax must both be given or both null");
+  AR_REQUIRE(q->dtype != AR_DT_NV_FP4 || gscale != nullptr, AR_E_BADARG, "nv_fp4 needs gscale");
+  const QArgs a = make_args(q, w, v, mn, mx, wmin, wmax, gscale);
+  const int64_t chunks = (int64_t)a.n * (a.kpad / 8);
+  const dim3 grid((unsigned)((chunks + kThreads - 1) / kThreads));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = q->group_size;
+  if (q->dtype == AR_DT_INT_SYM) {
+    launch_fwd_g<IntSym, false, SCALE_F16>(g, grid, st, a, (uint16_t*)wq, scale_out, nullptr);
+  } else if (q->dtype == AR_DT_INT_ASYM) {
+    launch_fwd_g<IntAsym, false, SCALE_F16>(g, grid, st, a, (uint16_t*)wq, scale_out, zp_out);
+  } else if (q->dtype == AR_DT_MX_FP4) {
+    launch_fwd_g<MxFp4, true, SCALE_BF16>(g, grid, st, a, (uint16_t*)wq, scale_out, nullptr);
+  } else {
+    launch_fwd_g<NvFp4, true, SCALE_F32>(g, grid, st, a, (uint16_t*)wq, scale_out, nullptr);
+  }
+  AR_CHECK_LAUNCH();
+  return AR_OK;
+}
+
+extern "C" int ar_qdq_bwd(const ar_qspec* q, const void* w, const float* v, const float* mn, const float* mx,
+                          const void* wmin, const void* wmax, const float* gscale, const float* gq, float* dv,
+                          float* dmin, float* dmax, int accumulate, void* stream) {
+  if (int rc = check_spec(q)) return rc;
+  AR_REQUIRE(w && gq && dv, AR_E_BADARG, "w/gq/dv must be non-null");
+  AR_REQUIRE((wmin == nullptr) == (wmax == nullptr), AR_E_BADARG, "wmin/wmax must both be given or both null");
+  AR_REQUIRE(q->dtype != AR_DT_NV_FP4 || gscale != nullptr, AR_E_BADARG, "nv_fp4 needs gscale");
+  const QArgs a = make_args(q, w, v, mn, mx, wmin, wmax, gscale);
+  const int64_t chunks = (int64_t)a.n * (a.kpad / 8);
+  const dim3 grid((unsigned)((chunks + kThreads - 1) / kThreads));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = q->group_size;
+  if (q->dtype == AR_DT_INT_SYM) {
+    launch_bwd_g<IntSym, false>(g, grid, st, a, gq, dv, dmin, dmax, accumulate);
+  } else if (q->dtype == AR_DT_INT_ASYM) {
+    launch_bwd_g<IntAsym, false>(g, grid, st, a, gq, dv, dmin, dmax, accumulate);
+  } else if (q->dtype == AR_DT_MX_FP4) {
+    launch_bwd_g<MxFp4, true>(g, grid, st, a, gq, dv, dmin, dmax, accumulate);
+  } else {
+    launch_bwd_g<NvFp4, true>(g, grid, st, a, gq, dv, dmin, dmax, accumulate);
+  }
+  AR_CHECK_LAUNCH();
+  return AR_OK;
+}
+
+extern "C" int ar_group_minmax(const ar_qspec* q, const void* w, void* wmin, void* wmax, void* stream) {
+  if (int rc = check_spec(q)) return rc;
+  AR_REQUIRE(w && wmin && wmax, AR_E_BADARG, "null pointer");
+  const QArgs a = make_args(q, w, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  const int64_t chunks = (int64_t)a.n * (a.kpad / 8);
+  const dim3 grid((unsigned)((chunks + kThreads - 1) / kThreads));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (q->group_size) {
+    case 16: group_minmax_kernel<16><<<grid, kThreads, 0, st>>>(a, (uint16_t*)wmin, (uint16_t*)wmax); break;
+    case 32: group_minmax_kernel<32><<<grid, kThreads, 0, st>>>(a, (uint16_t*)wmin, (uint16_t*)wmax); break;
+    case 64: group_minmax_kernel<64><<<grid, kThreads, 0, st>>>(a, (uint16_t*)wmin, (uint16_t*)wmax); break;
+    case 128: group_minmax_kernel<128><<<grid, kThreads, 0, st>>>(a, (uint16_t*)wmin, (uint16_t*)wmax); break;
+    default: group_minmax_kernel<256><<<grid, kThreads, 0, st>>>(a, (uint16_t*)wmin, (uint16_t*)wmax); break;
+  }
+  AR_CHECK_LAUNCH();
+  return AR_OK;
+}
+
+extern "C" int ar_absmax(const void* w, int64_t numel, float* amax, void* stream) {
+  AR_REQUIRE(w && amax && numel > 0, AR_E_BADARG, "bad args");
+  const int blocks = (int)((numel + 256 * 16 - 1) / (256 * 16));
+  absmax_kernel<<<blocks < 2048 ? (blocks > 0 ? blocks : 1) : 2048, 256, 0, (cudaStream_t)stream>>>(
+      (const uint16_t*)w, numel, amax);
+  AR_CHECK_LAUNCH();
+  return AR_OK;
+}
+extern "C" int ar_nv_global_scale(const float* amax, float* gs, void* stream) {
+  AR_REQUIRE(amax && gs, AR_E_BADARG, "bad args");
+  nv_gscale_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(amax, gs);
+  AR_CHECK_LAUNCH();
+  return AR_OK;
+}
+
+// one-to-one aliases of the reference's @register_dtype names
+extern "C" int ar_qdq_int_sym_fwd(const ar_qspec* q, const void* w, const float* v, const float* mn, const float* mx,
+                                  const void* wmin, const void* wmax, void* wq, void* scale, void* stream) {
+  ar_qspec s = *q; s.dtype = AR_DT_INT_SYM;
+  return ar_qdq_fwd(&s, w, v, mn, mx, wmin, wmax, nullptr, wq, scale, nullptr, stream);
+}
+extern "C" int ar_qdq_int_asym_fwd(const ar_qspec* q, const void* w, const float* v, const float* mn,
+                                   const float* mx, const void* wmin, const void* wmax, void* wq, void* scale,
+                                   float* zp, void* stream) {
+  ar_qspec s = *q; s.dtype = AR_DT_INT_ASYM;
+  return ar_qdq_fwd(&s, w, v, mn, mx, wmin, wmax, nullptr, wq, scale, zp, stream);
+}
+extern "C" int ar_qdq_mx_fp4_fwd(const ar_qspec* q, const void* w, const float* v, const float* mx, void* wq,
+                                 void* exp_out, void* stream) {
+  ar_qspec s = *q; s.dtype = AR_DT_MX_FP4;
+  return ar_qdq_fwd(&s, w, v, nullptr, mx, nullptr, nullptr, nullptr, wq, exp_out, nullptr, stream);
+}
+extern "C" int ar_qdq_nv_fp4_fwd(const ar_qspec* q, const void* w, const float* v, const float* mx,
+                                 const float* gscale, void* wq, void* scale, void* stream) {
+  ar_qspec s = *q; s.dtype = AR_DT_NV_FP4;
+  return ar_qdq_fwd(&s, w, v, nullptr, mx, nullptr, nullptr, gscale, wq, scale, nullptr, stream);
+}

@@ -1,0 +1,235 @@
+// Device-side fake-quant numerics shared by the standalone qdq kernels (ar_qdq.cu) and the fused
+// epilogue of the dW GEMM (ar_gemm.cu).  One struct per AutoRound data type:
+//
+//     Ctx::setup(group inputs)        once per quantisation group
+//     ctx.fwd(w, v)                   -> dequantised value (fp32, before the bf16 cast)
+//     ctx.bwd(w, v, gq, dv, acc)      -> dL/dV for this element, group partial sums in `acc`
+//     ctx.finish(acc, dmin, dmax)     -> dL/d(min_scale), dL/d(max_scale) of the group
+//
+// Every expression mirrors the reference's torch op sequence in fp32 (IEEE div, half-to-even rint, no FMA
+// contraction: the library is compiled with -fmad=false) so that round(W/s + V) is bit-identical:
+//   int_sym  auto_round/data_type/int.py:165-238      int_asym auto_round/data_type/int.py:241-298
+//   mx_fp4   auto_round/data_type/mxfp.py:49-85,233-291   nv_fp4 auto_round/data_type/nvfp.py:26-98
+// The backward formulas are the closed form of torch autograd over those graphs (straight-through
+// estimators: auto_round/data_type/utils.py:314-365); derivation in DESIGN.md section 4.
+#pragma once
+#include "ar_common.cuh"
+
+namespace ar {
+
+struct GroupIn {
+  float wmin, wmax;  // int types: min/max of the group clamped at 0 (bf16 values); fp4: wmax = amax|W|
+  float mn, mx;      // min_scale / max_scale of the group (1 when absent)
+  float gscale;      // NVFP4 per-tensor global scale
+  float thr;         // q_scale_thresh
+};
+
+struct GroupAcc {
+  float a = 0.f, b = 0.f;  // meaning is per data type (see bwd/finish)
+};
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// ------------------------------------------------------------------------------------------------ int_sym
+struct IntSym {
+  float kMaxq;    // 2^(bits-1)
+  float s;        // scale: fp16-rounded, threshold-clipped, as fp32
+  float route_mx; // d s_raw / d max_scale
+  float route_mn; // d s_raw / d min_scale
+
+  __device__ __forceinline__ void init(int bits) { kMaxq = (float)(1 << (bits - 1)); }
+  __device__ __forceinline__ void setup(const GroupIn& g) {
+    const float lo = -(g.wmin * g.mn);
+    const float hi = g.wmax * g.mx;
+    const float sgn = (hi < lo) ? 1.f : -1.f;        // "full range": +max maps to -maxq  (int.py:228-230)
+    const float s_raw = f16_round((sgn * fmaxf(hi, lo)) / kMaxq);
+    const float thr = f16_round(g.thr);               // clamp runs in the fp16 tensor's dtype
+    bool pass;
+    if (s_raw < 0.f) { s = fminf(s_raw, -thr); pass = (s_raw <= -thr); }
+    else             { s = fmaxf(s_raw, thr);  pass = (s_raw >= thr); }
+    // torch.max(hi, lo) backward: winner takes all, ties split evenly
+    const float whi = hi > lo ? 1.f : (hi == lo ? 0.5f : 0.f);
+    const float base = pass ? (sgn / kMaxq) : 0.f;
+    route_mx = base * whi * g.wmax;
+    route_mn = base * (1.f - whi) * (-g.wmin);
+  }
+  __device__ __forceinline__ float code(float w, float v) const {   // q in [-maxq, maxq-1]
+    return clampf(rintf(w / s + v), -kMaxq, kMaxq - 1.f);
+  }
+  __device__ __forceinline__ float fwd(float w, float v) const { return s * code(w, v); }
+  __device__ __forceinline__ void bwd(float w, float v, float gq, float& dv, GroupAcc& acc) const {
+    const float ws = w / s;
+    const float r = rintf(ws + v);
+    const bool in = (r >= -kMaxq) && (r <= kMaxq - 1.f);
+    const float q = clampf(r, -kMaxq, kMaxq - 1.f);
+    const float dt = in ? gq * s : 0.f;
+    dv = dt;
+    acc.a += gq * q - dt * (ws / s);                                 // d L / d s
+  }
+  __device__ __forceinline__ void finish(const GroupAcc& acc, const GroupIn&, float& dmin, float& dmax) const {
+    dmax = acc.a * route_mx;
+    dmin = acc.a * route_mn;
+  }
+  __device__ __forceinline__ float scale_out() const { return s; }
+  __device__ __forceinline__ float zp_out() const { return kMaxq; }
+};
+
+// ----------------------------------------------------------------------------------------------- int_asym
+struct IntAsym {
+  float kMaxq;    // 2^bits - 1
+  float s, zp, lo;
+  bool pass;
+
+  __device__ __forceinline__ void init(int bits) { kMaxq = (float)((1 << bits) - 1); }
+  __device__ __forceinline__ void setup(const GroupIn& g) {
+    lo = g.wmin * g.mn;
+    const float hi = g.wmax * g.mx;
+    const float s_raw = f16_round((hi - lo) / kMaxq);
+    const float thr = f16_round(g.thr);
+    s = fmaxf(s_raw, thr);
+    pass = (s_raw >= thr);
+    zp = rintf((-lo) / s);
+  }
+  __device__ __forceinline__ float code(float w, float v) const {   // q in [0, maxq]
+    return clampf(rintf(w / s + v) + zp, 0.f, kMaxq);
+  }
+  __device__ __forceinline__ float fwd(float w, float v) const { return s * (code(w, v) - zp); }
+  __device__ __forceinline__ void bwd(float w, float v, float gq, float& dv, GroupAcc& acc) const {
+    const float ws = w / s;
+    const float u = rintf(ws + v) + zp;
+    const bool in = (u >= 0.f) && (u <= kMaxq);
+    const float q = clampf(u, 0.f, kMaxq);
+    const float gs = gq * s;
+    const float dt = in ? gs : 0.f;
+    dv = dt;
+    acc.a += gq * (q - zp) - dt * (ws / s);                          // d L / d s  (direct + through W/s)
+    acc.b += dt - gs;                                                // d L / d zp (clamped elements only)
+  }
+  __device__ __forceinline__ void finish(const GroupAcc& acc, const GroupIn& g, float& dmin, float& dmax) const {
+    const float dzp = acc.b;
+    // zp = round_ste(-lo / s):  d(-lo) = dzp / s ,  d s += -dzp * ((-lo / s) / s)
+    const float ds = acc.a - dzp * (((-lo) / s) / s);
+    const float ds_raw = pass ? ds : 0.f;
+    const float dhi = ds_raw / kMaxq;
+    const float dlo = -(dzp / s) - ds_raw / kMaxq;
+    dmax = dhi * g.wmax;
+    dmin = dlo * g.wmin;
+  }
+  __device__ __forceinline__ float scale_out() const { return s; }
+  __device__ __forceinline__ float zp_out() const { return zp; }
+};
+
+// ------------------------------------------------------------------------------------------------- mx_fp4
+__device__ __forceinline__ float py_mod2(float x) {   // torch.remainder(x, 2): result takes the divisor's sign
+  float r = fmodf(x, 2.f);
+  if (r != 0.f && r < 0.f) r += 2.f;
+  return r;
+}
+
+// E2M1 element rounding, auto_round/data_type/mxfp.py:49-85 with ebits=2, mbits=3, max_norm=6
+__device__ __forceinline__ float mx_quant_element(float t) {
+  const float a0 = fabsf(t) + (t == 0.f ? 1.f : 0.f);
+  const float p = a0 >= 4.f ? 4.f : (a0 >= 2.f ? 2.f : 1.f);          // 2^max(floor(log2 a0), 0) for a0 <= 6
+  const float y = t / p * 2.f;
+  const float a = fabsf(y);
+  const float tie = (py_mod2(a - 0.5f) == 0.f) ? 1.f : 0.f;
+  const float sg = (y > 0.f) ? 1.f : (y < 0.f ? -1.f : 0.f);
+  const float r = sg * (floorf(a + 0.5f) - tie);
+  return clampf(r / 2.f * p, -6.f, 6.f);
+}
+
+struct MxFp4 {
+  __device__ __forceinline__ void init(int) {}
+  float s;      // 2^e
+  float e;      // shared exponent (after -emax and clamp)
+  float m;      // amax * max_scale
+  bool pass;
+
+  __device__ __forceinline__ void setup(const GroupIn& g) {
+    m = g.wmax * g.mx;
+    const float e_raw = (m == 0.f) ? 1.f : log2f(m);
+    const float ef = floorf(e_raw) - 2.f;
+    e = clampf(ef, -127.f, 127.f);
+    pass = (ef >= -127.f) && (ef <= 127.f) && (m != 0.f);
+    s = ldexpf(1.f, (int)e);
+  }
+  __device__ __forceinline__ float fwd(float w, float v) const {
+    const float t = clampf(w / s + v, -6.f, 6.f);
+    return mx_quant_element(t) * s;
+  }
+  __device__ __forceinline__ void bwd(float w, float v, float gq, float& dv, GroupAcc& acc) const {
+    const float ws = w / s;
+    const float t = ws + v;
+    const bool in = (t >= -6.f) && (t <= 6.f);
+    const float tc = clampf(t, -6.f, 6.f);
+    const float o = mx_quant_element(tc);
+    // d o / d tc through quant_element's graph: 1 below |tc| < 1 (0 at exactly 0), o/tc above
+    const float f = (fabsf(tc) >= 1.f) ? (o / tc) : (tc != 0.f ? 1.f : 0.f);
+    const float dt = in ? gq * s * f : 0.f;
+    dv = dt;
+    acc.a += gq * o - dt * (ws / s);                                  // d L / d s
+  }
+  __device__ __forceinline__ void finish(const GroupAcc& acc, const GroupIn& g, float& dmin, float& dmax) const {
+    // s = 2^e, e = floor_ste(log2 m) - 2  =>  ds/dm = s / m ;  m = amax * max_scale
+    dmax = pass ? acc.a * (s / m) * g.wmax : 0.f;
+    dmin = 0.f;
+  }
+  __device__ __forceinline__ float scale_out() const { return e; }
+  __device__ __forceinline__ float zp_out() const { return 0.f; }
+};
+
+// ------------------------------------------------------------------------------------------------- nv_fp4
+// cast_to_fp4, auto_round/data_type/nvfp.py:26-39
+__device__ __forceinline__ float nv_cast_to_fp4(float x) {
+  const float sg = (x > 0.f) ? 1.f : (x < 0.f ? -1.f : 0.f);
+  const float a = fabsf(x);
+  float r;
+  if (a < 2.f) r = rintf(2.f * a) / 2.f;
+  else if (a < 4.f) r = rintf(a);
+  else r = 2.f * rintf(a / 2.f);
+  return clampf(r, -6.f, 6.f) * sg;
+}
+
+struct NvFp4 {
+  __device__ __forceinline__ void init(int) {}
+  float sc;     // e4m3-valued block scale (fp32)
+  float inv;    // 1 / (sc / gscale)   (0 when sc == 0)
+  float rinv;   // 1 / inv
+  float route;  // d inv / d max_scale
+
+  __device__ __forceinline__ void setup(const GroupIn& g) {
+    const float vmax = g.wmax * g.mx;
+    const float sc_raw = g.gscale * (vmax * 0.16666667163372040f);     // get_reciprocal(6.0) as fp32
+    const float sc_c = clampf(sc_raw, -448.f, 448.f);
+    sc = e4m3_bits_to_f32(f32_to_e4m3_bits(sc_c));
+    const float rg = (g.gscale == 0.f) ? 0.f : 1.f / g.gscale;
+    const float prod = sc * rg;
+    inv = (prod == 0.f) ? 0.f : 1.f / prod;
+    rinv = (inv == 0.f) ? 0.f : 1.f / inv;
+    const bool pass = (sc_raw >= -448.f) && (sc_raw <= 448.f);
+    // inv = 1/prod, prod = sc*rg, sc = gs*vmax/6 (STE through e4m3), vmax = amax*mx
+    route = (prod != 0.f && pass) ? (-(inv / prod)) * rg * g.gscale * 0.16666667163372040f * g.wmax : 0.f;
+  }
+  __device__ __forceinline__ float fwd(float w, float v) const {
+    const float x = clampf(w * inv + v, -6.f, 6.f);
+    return nv_cast_to_fp4(x) * rinv;
+  }
+  __device__ __forceinline__ void bwd(float w, float v, float gq, float& dv, GroupAcc& acc) const {
+    const float x = w * inv + v;
+    const bool in = (x >= -6.f) && (x <= 6.f);
+    const float xc = clampf(x, -6.f, 6.f);
+    const float c = nv_cast_to_fp4(xc);
+    const float dx = (in && xc != 0.f) ? gq * rinv : 0.f;            // d cast/d x = sign(x)^2
+    dv = dx;
+    // d L / d inv = dx*w (through x)  -  gq*c * rinv/inv (through 1/inv)
+    acc.a += dx * w - ((inv != 0.f) ? gq * c * (rinv / inv) : 0.f);
+  }
+  __device__ __forceinline__ void finish(const GroupAcc& acc, const GroupIn&, float& dmin, float& dmax) const {
+    dmax = acc.a * route;   // reference yields NaN (0*inf) for an all-zero group; we define it as 0
+    dmin = 0.f;
+  }
+  __device__ __forceinline__ float scale_out() const { return sc; }
+  __device__ __forceinline__ float zp_out() const { return 0.f; }
+};
+
+}  // namespace ar

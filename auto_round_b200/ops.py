@@ -1,0 +1,270 @@
+"""Thin torch-tensor front end over the C ABI (include/ar_b200.h).  PyTorch only owns the memory and the
+stream; every function below enqueues hand-written sm_100a kernels from libar_b200.so and returns.
+
+No function here has a CPU / eager fallback: tensors must be CUDA tensors and the library must load.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import DT_INT_ASYM, DT_INT_SYM, DT_MX_FP4, DT_NV_FP4, QSpec
+
+DTYPE_IDS = {"int_sym": DT_INT_SYM, "int_asym": DT_INT_ASYM, "mx_fp4": DT_MX_FP4, "nv_fp4": DT_NV_FP4}
+
+
+@dataclass(frozen=True)
+class Spec:
+    """Quantisation spec of one linear layer (mirror of struct ar_qspec)."""
+    dtype: int
+    bits: int
+    group_size: int
+    n: int
+    k: int
+    q_scale_thresh: float = 1e-5
+    scale_bound_hi: float = 1.0
+
+    @property
+    def kpad(self) -> int:
+        g = self.group_size
+        return (self.k + g - 1) // g * g
+
+    @property
+    def groups(self) -> int:
+        return self.n * (self.kpad // self.group_size)
+
+    @property
+    def is_int(self) -> bool:
+        return self.dtype in (DT_INT_SYM, DT_INT_ASYM)
+
+    def c(self) -> QSpec:
+        return QSpec(self.dtype, self.bits, self.group_size, self.n, self.k, self.q_scale_thresh, self.scale_bound_hi)
+
+
+def make_spec(name: str, bits: int, group_size: int, n: int, k: int, q_scale_thresh: float = 1e-5,
+              scale_bound_hi: float = 1.0) -> Spec:
+    return Spec(DTYPE_IDS[name], bits, group_size, n, k, q_scale_thresh, scale_bound_hi)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("auto_round_b200 kernels take CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _want(t, dtype, what):
+    if t is not None and t.dtype != dtype:
+        raise TypeError(f"{what}: expected {dtype}, got {t.dtype}")
+
+
+def group_minmax(spec: Spec, w: torch.Tensor):
+    """weight_min / weight_max per group, bf16 [G] (auto_round/wrapper.py:154-167)."""
+    _want(w, torch.bfloat16, "w")
+    wmin = torch.empty(spec.groups, dtype=torch.bfloat16, device=w.device)
+    wmax = torch.empty_like(wmin)
+    cs = spec.c()
+    _lib.check(_lib.load().ar_group_minmax(C.byref(cs), _p(w), _p(wmin), _p(wmax), _stream()), "ar_group_minmax")
+    return wmin, wmax
+
+
+def nv_global_scale(w: torch.Tensor) -> torch.Tensor:
+    """448*6/amax(|W|) as a device fp32 scalar (auto_round/data_type/nvfp.py:56-64)."""
+    _want(w, torch.bfloat16, "w")
+    amax = torch.zeros(1, dtype=torch.float32, device=w.device)
+    gs = torch.empty(1, dtype=torch.float32, device=w.device)
+    lib = _lib.load()
+    _lib.check(lib.ar_absmax(_p(w), w.numel(), _p(amax), _stream()), "ar_absmax")
+    _lib.check(lib.ar_nv_global_scale(_p(amax), _p(gs), _stream()), "ar_nv_global_scale")
+    return gs
+
+
+def scale_dtype_of(spec: Spec):
+    return {DT_INT_SYM: torch.float16, DT_INT_ASYM: torch.float16, DT_MX_FP4: torch.bfloat16,
+            DT_NV_FP4: torch.float32}[spec.dtype]
+
+
+def qdq_fwd(spec: Spec, w, v=None, min_scale=None, max_scale=None, wmin=None, wmax=None, gscale=None,
+            out_wq=None, want_wq=True, want_scale=False):
+    """Fake-quant forward.  Returns (wq bf16 [N,K] | None, scale [G] | None, zp fp32 [G] | None)."""
+    _want(w, torch.bfloat16, "w")
+    for t, nm in ((v, "v"), (min_scale, "min_scale"), (max_scale, "max_scale"), (gscale, "gscale")):
+        _want(t, torch.float32, nm)
+    wq = (out_wq if out_wq is not None else torch.empty_like(w)) if want_wq else None
+    scale = torch.empty(spec.groups, dtype=scale_dtype_of(spec), device=w.device) if want_scale else None
+    zp = torch.empty(spec.groups, dtype=torch.float32, device=w.device) if (want_scale and spec.dtype == DT_INT_ASYM) else None
+    cs = spec.c()
+    _lib.check(_lib.load().ar_qdq_fwd(C.byref(cs), _p(w), _p(v), _p(min_scale), _p(max_scale), _p(wmin), _p(wmax),
+                                      _p(gscale), _p(wq), _p(scale), _p(zp), _stream()), "ar_qdq_fwd")
+    return wq, scale, zp
+
+
+def qdq_bwd(spec: Spec, w, gq, v=None, min_scale=None, max_scale=None, wmin=None, wmax=None, gscale=None,
+            dv=None, dmin=None, dmax=None, accumulate=False):
+    """Fake-quant backward: Gq fp32 [N,K] -> (dv fp32 [N,Kpad], dmin [G] | None, dmax [G])."""
+    _want(w, torch.bfloat16, "w")
+    _want(gq, torch.float32, "gq")
+    dev = w.device
+    if dv is None:
+        dv = torch.empty(spec.n, spec.kpad, dtype=torch.float32, device=dev)
+    if dmax is None:
+        dmax = torch.empty(spec.groups, dtype=torch.float32, device=dev)
+    if dmin is None and spec.is_int:
+        dmin = torch.empty(spec.groups, dtype=torch.float32, device=dev)
+    cs = spec.c()
+    _lib.check(_lib.load().ar_qdq_bwd(C.byref(cs), _p(w), _p(v), _p(min_scale), _p(max_scale), _p(wmin), _p(wmax),
+                                      _p(gscale), _p(gq), _p(dv), _p(dmin), _p(dmax), int(accumulate), _stream()),
+               "ar_qdq_bwd")
+    return dv, dmin, dmax
+
+
+def gemm(a, b, a_mn_major=False, b_mn_major=False, bias=None, out=None):
+    """D[M,N] = A·Bᵀ on tcgen05.  A is [M,K] (or stored [K,M] if a_mn_major), B is [N,K] (or stored [K,N])."""
+    _want(a, torch.bfloat16, "a")
+    _want(b, torch.bfloat16, "b")
+    if a_mn_major:
+        k, m = a.shape
+    else:
+        m, k = a.shape
+    if b_mn_major:
+        kb, n = b.shape
+    else:
+        n, kb = b.shape
+    if kb != k:
+        raise ValueError(f"reduction dims differ: {k} vs {kb}")
+    d = out if out is not None else torch.empty(m, n, dtype=torch.bfloat16, device=a.device)
+    _lib.check(_lib.load().ar_gemm_bf16(_p(a), _p(b), _p(d), m, n, k, int(a_mn_major), int(b_mn_major),
+                                        a.stride(0), b.stride(0), d.stride(0), _p(bias), _stream()), "ar_gemm_bf16")
+    return d
+
+
+def fq_linear_fwd(spec: Spec, x2d, w, v, min_scale, max_scale, wmin, wmax, gscale, bias, wq_scratch, out=None):
+    _want(x2d, torch.bfloat16, "x")
+    t = x2d.shape[0]
+    y = out if out is not None else torch.empty(t, spec.n, dtype=torch.bfloat16, device=x2d.device)
+    cs = spec.c()
+    _lib.check(_lib.load().ar_fq_linear_fwd(C.byref(cs), _p(x2d), t, _p(w), _p(v), _p(min_scale), _p(max_scale), _p(wmin),
+                                            _p(wmax), _p(gscale), _p(bias), _p(wq_scratch), _p(y), _stream()),
+               "ar_fq_linear_fwd")
+    return y
+
+
+def fq_linear_bwd_dx(spec: Spec, dy2d, wq, out=None):
+    _want(dy2d, torch.bfloat16, "dy")
+    t = dy2d.shape[0]
+    dx = out if out is not None else torch.empty(t, spec.k, dtype=torch.bfloat16, device=dy2d.device)
+    cs = spec.c()
+    _lib.check(_lib.load().ar_fq_linear_bwd_dx(C.byref(cs), _p(dy2d), t, _p(wq), _p(dx), _stream()), "ar_fq_linear_bwd_dx")
+    return dx
+
+
+def fq_linear_bwd_dw(spec: Spec, dy2d, x2d, w, v, min_scale, max_scale, wmin, wmax, gscale, dv, dmin, dmax,
+                     accumulate=False):
+    _want(dy2d, torch.bfloat16, "dy")
+    _want(x2d, torch.bfloat16, "x")
+    cs = spec.c()
+    _lib.check(_lib.load().ar_fq_linear_bwd_dw(C.byref(cs), _p(dy2d), _p(x2d), dy2d.shape[0], _p(w), _p(v), _p(min_scale),
+                                               _p(max_scale), _p(wmin), _p(wmax), _p(gscale), _p(dv), _p(dmin), _p(dmax),
+                                               int(accumulate), _stream()), "ar_fq_linear_bwd_dw")
+
+
+def mse_fwd_bwd(pred2d, ref2d, row_mask, inv_numel, upstream, loss_sum, dpred=None, want_grad=True):
+    """loss_sum (double [1]) += sum(((pred-ref)*m)^2); returns dpred bf16 (see include/ar_b200.h)."""
+    _want(pred2d, torch.bfloat16, "pred")
+    _want(ref2d, torch.bfloat16, "ref")
+    _want(loss_sum, torch.float64, "loss_sum")
+    _want(row_mask, torch.uint8, "row_mask")
+    rows, cols = pred2d.shape
+    if want_grad and dpred is None:
+        dpred = torch.empty_like(pred2d)
+    _lib.check(_lib.load().ar_mse_fwd_bwd(_p(pred2d), _p(ref2d), _p(row_mask), rows, cols, float(inv_numel), float(upstream),
+                                          _p(loss_sum), _p(dpred) if want_grad else None, _stream()), "ar_mse_fwd_bwd")
+    return dpred
+
+
+def best_update(loss_sum, inv_numel, inv_num_elm, it, state, flag, loss_hist):
+    _lib.check(_lib.load().ar_best_update(_p(loss_sum), float(inv_numel), float(inv_num_elm), int(it), _p(state), _p(flag),
+                                          _p(loss_hist), _stream()), "ar_best_update")
+
+
+def signsgd_step(p, g, best, flag, lr_table, it, clamp_begin, clamp_hi=1.0):
+    _want(p, torch.float32, "p")
+    _want(g, torch.float32, "g")
+    _lib.check(_lib.load().ar_signsgd_step(_p(p), _p(g), _p(best), _p(flag), _p(lr_table), int(it), p.numel(),
+                                           int(clamp_begin), float(clamp_hi), _stream()), "ar_signsgd_step")
+
+
+def gather_rows(src, idx_i32, out=None):
+    """out[i] = src[idx[i]] for a [S, ...] bf16 tensor of cached samples."""
+    _want(src, torch.bfloat16, "src")
+    _want(idx_i32, torch.int32, "idx")
+    count = idx_i32.numel()
+    row = src[0].numel()
+    if out is None:
+        out = torch.empty((count,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    _lib.check(_lib.load().ar_gather_rows(_p(src), _p(idx_i32), count, row, _p(out), _stream()), "ar_gather_rows")
+    return out
+
+
+def pack_int(wq, scale_f16, zp, bits, group_size, zp_minus_one, zp_const=0):
+    """-> qweight i32 [K*bits/32,N], qzeros i32 [G',N*bits/32], scales fp16 [G',N], g_idx i32 [K]."""
+    _want(wq, torch.bfloat16, "wq")
+    _want(scale_f16, torch.float16, "scale")
+    _want(zp, torch.float32, "zp")
+    n, k = wq.shape
+    g = k if group_size in (-1, 0) else group_size
+    ng = (k + g - 1) // g
+    dev = wq.device
+    qweight = torch.empty(k * bits // 32, n, dtype=torch.int32, device=dev)
+    qzeros = torch.empty(ng, n * bits // 32, dtype=torch.int32, device=dev)
+    scales_t = torch.empty(ng, n, dtype=torch.float16, device=dev)
+    g_idx = torch.empty(k, dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().ar_pack_int(_p(wq), _p(scale_f16), _p(zp), int(zp_const), n, k, bits, g, int(zp_minus_one),
+                                       _p(qweight), _p(qzeros), _p(scales_t), _p(g_idx), _stream()), "ar_pack_int")
+    return qweight, qzeros, scales_t, g_idx
+
+
+def unpack_int(qweight, qzeros, scales_t, n, k, bits, group_size, zp_minus_one, want_codes=False):
+    g = k if group_size in (-1, 0) else group_size
+    w = torch.empty(n, k, dtype=torch.bfloat16, device=qweight.device)
+    codes = torch.empty(n, k, dtype=torch.int32, device=qweight.device) if want_codes else None
+    _lib.check(_lib.load().ar_unpack_int(_p(qweight), _p(qzeros), _p(scales_t), n, k, bits, g, int(zp_minus_one), _p(w),
+                                         _p(codes), _stream()), "ar_unpack_int")
+    return w, codes
+
+
+def pack_fp4_nv(wq, scale_f32, gscale):
+    _want(wq, torch.bfloat16, "wq")
+    _want(scale_f32, torch.float32, "scale")
+    n, k = wq.shape
+    packed = torch.empty(n, k // 2, dtype=torch.uint8, device=wq.device)
+    sc = torch.empty(n, k // 16, dtype=torch.uint8, device=wq.device)
+    _lib.check(_lib.load().ar_pack_fp4_nv(_p(wq), _p(scale_f32), _p(gscale), n, k, _p(packed), _p(sc), _stream()),
+               "ar_pack_fp4_nv")
+    return packed, sc
+
+
+def pack_fp4_mx(wq, exp_bf16):
+    _want(wq, torch.bfloat16, "wq")
+    _want(exp_bf16, torch.bfloat16, "exp")
+    n, k = wq.shape
+    packed = torch.empty(n, k // 2, dtype=torch.uint8, device=wq.device)
+    sc = torch.empty(n, k // 32, dtype=torch.uint8, device=wq.device)
+    _lib.check(_lib.load().ar_pack_fp4_mx(_p(wq), _p(exp_bf16), n, k, _p(packed), _p(sc), _stream()), "ar_pack_fp4_mx")
+    return packed, sc
+
+
+def unpack_fp4(packed, n, k):
+    out = torch.empty(n, k, dtype=torch.bfloat16, device=packed.device)
+    _lib.check(_lib.load().ar_unpack_fp4(_p(packed), n, k, _p(out), _stream()), "ar_unpack_fp4")
+    return out

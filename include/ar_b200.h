@@ -1,0 +1,200 @@
+/*
+ * ar_b200.h -- C ABI of the B200-native AutoRound calibration kernels (libar_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of intel/auto-round: the per-block SignRound tuning loop, its
+ * weight quant-dequant numerics and the final low-bit pack.  The reference has no native code on this
+ * path (it is eager PyTorch); each entry point below names the reference Python it replaces
+ * (paths relative to the reference root, v0.15.0).  INTEGRATION.md shows the ctypes binding a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory;
+ *   - no entry point allocates, synchronises with the host, or keeps global state (a small cache of
+ *     cuTensorMap descriptors keyed by pointer/shape is the one exception, see ar_gemm_*);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the call returns;
+ *   - return value: 0 = ok, <0 = argument error (AR_E_*), >0 = a cudaError_t from the launch;
+ *     ar_last_error() gives a thread-local message.  No exceptions cross the ABI;
+ *   - W is the nn.Linear weight [N, K] (out x in) row-major bf16; quantisation groups run along K
+ *     inside a row (group index = n * ceil(K/g) + k / g), exactly as
+ *     auto_round/data_type/utils.py:29-71 (reshape_pad_tensor_by_group_size) lays them out;
+ *   - V (the learnable rounding offset) is fp32 [N, Kpad], Kpad = ceil(K/g)*g; min_scale/max_scale
+ *     are fp32 [G], G = N * Kpad / g  (auto_round/wrapper.py:184-190).
+ */
+#ifndef AR_B200_H_
+#define AR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AR_B200_VERSION 100
+
+/* data types of the fake-quant functions (auto_round/data_type/register.py names) */
+enum {
+  AR_DT_INT_SYM = 0,  /* "int_sym"  auto_round/data_type/int.py:165-238  */
+  AR_DT_INT_ASYM = 1, /* "int_asym" auto_round/data_type/int.py:241-298  */
+  AR_DT_MX_FP4 = 2,   /* "mx_fp4"   auto_round/data_type/mxfp.py:233-291 */
+  AR_DT_NV_FP4 = 3    /* "nv_fp4"   auto_round/data_type/nvfp.py:83-98   */
+};
+
+enum {
+  AR_OK = 0,
+  AR_E_BADARG = -1,     /* null pointer / shape not supported */
+  AR_E_UNSUPPORTED = -2,/* combination not built (e.g. group size) */
+  AR_E_NOTSM100 = -3,   /* tcgen05 path requested on a non-sm_100 device */
+  AR_E_DRIVER = -4      /* cuTensorMapEncodeTiled unavailable / failed */
+};
+
+int ar_version(void);
+const char* ar_last_error(void);
+
+/* Quantisation spec of one linear layer.  Plain-old-data, passed by pointer (host memory). */
+typedef struct ar_qspec {
+  int32_t dtype;          /* AR_DT_* */
+  int32_t bits;           /* 2,3,4,8 for int; 4 for fp4 */
+  int32_t group_size;     /* 16/32/64/128/256; K is zero-padded to a multiple (reference semantics) */
+  int32_t n;              /* rows of W (out features) */
+  int32_t k;              /* cols of W (in features) */
+  float q_scale_thresh;   /* 1e-5 (fp16 scale) / 1e-8 (fp32 scale): auto_round/wrapper.py:115-118 */
+  float scale_bound_hi;   /* upper clamp of min/max_scale: 1.0 (wrapper.py:76) or 2.0 (alg_ext) */
+} ar_qspec;
+
+/* Per-group min/max of W clamped at 0 (bf16 out, [G]) -- auto_round/wrapper.py:154-167. */
+int ar_group_minmax(const ar_qspec* q, const void* w_bf16, void* wmin_bf16, void* wmax_bf16, void* stream);
+
+/* amax(|W|) over the whole tensor into *amax_f32 (atomicMax on the bit pattern; caller zeroes it first),
+ * and NVFP4 global scale 448*6/amax -- auto_round/data_type/nvfp.py:56-64 (calculate_gparam). */
+int ar_absmax(const void* w_bf16, int64_t numel, float* amax_f32, void* stream);
+int ar_nv_global_scale(const float* amax_f32, float* gscale_f32, void* stream);
+
+/*
+ * Fake-quant forward: Wq = qdq(W; V, min_scale, max_scale).  Replaces WrapperLinear._qdq_weight
+ * (auto_round/wrapper.py:244-293) + the registered data_type function, for all AR_DT_*.
+ *   v, min_scale, max_scale may be NULL (=> 0, 1, 1: plain RTN, auto_round/data_type/int.py:125-162).
+ *   wmin/wmax: bf16 [G] from ar_group_minmax (int types; ignored for fp4, which use amax|W| per group).
+ *   gscale: device fp32 scalar (nv_fp4 only).
+ *   wq_bf16 [N,K] may be NULL if only scales are wanted.
+ *   scale_out: fp16 [G] (int) | bf16 [G] shared exponent (mx) | fp32 [G] e4m3-valued (nv); may be NULL.
+ *   zp_out:    fp32 [G] (int_asym only); may be NULL.
+ */
+int ar_qdq_fwd(const ar_qspec* q, const void* w_bf16, const float* v, const float* min_scale,
+               const float* max_scale, const void* wmin_bf16, const void* wmax_bf16, const float* gscale,
+               void* wq_bf16, void* scale_out, float* zp_out, void* stream);
+
+/*
+ * Fake-quant backward (what autograd does through the reference's qdq graph, auto_round/wrapper.py:273-290
+ * + STE helpers auto_round/data_type/utils.py:314-365): given Gq = dL/dWq fp32 [N,K] produce
+ *   dv [N,Kpad] fp32, dmin [G] fp32 (int types; NULL otherwise), dmax [G] fp32.
+ *   accumulate != 0 adds into the outputs (gradient accumulation), else overwrites.
+ */
+int ar_qdq_bwd(const ar_qspec* q, const void* w_bf16, const float* v, const float* min_scale,
+               const float* max_scale, const void* wmin_bf16, const void* wmax_bf16, const float* gscale,
+               const float* gq_f32, float* dv, float* dmin, float* dmax, int accumulate, void* stream);
+
+/* named aliases the reference-side registry would bind one-to-one (@register_dtype names) */
+int ar_qdq_int_sym_fwd(const ar_qspec*, const void*, const float*, const float*, const float*, const void*,
+                       const void*, void*, void*, void*);
+int ar_qdq_int_asym_fwd(const ar_qspec*, const void*, const float*, const float*, const float*, const void*,
+                        const void*, void*, void*, float*, void*);
+int ar_qdq_mx_fp4_fwd(const ar_qspec*, const void*, const float*, const float*, void*, void*, void*);
+int ar_qdq_nv_fp4_fwd(const ar_qspec*, const void*, const float*, const float*, const float*, void*, void*, void*);
+
+/*
+ * bf16 GEMM on tcgen05/TMA:  D[M,N] = A · Bᵀ  with A logical [M,K], B logical [N,K].
+ *   a_mn_major / b_mn_major = 0: operand stored [rows, K] row-major (K contiguous);
+ *                            = 1: operand stored [K, rows] row-major (rows contiguous).
+ *   lda/ldb/ldd: leading dimension (elements) of the stored matrix.  D is bf16 row-major [M,N].
+ *   bias_bf16: optional [N] added in the epilogue.  Replaces F.linear (auto_round/wrapper.py:470-481)
+ *   and its two autograd GEMMs.
+ */
+int ar_gemm_bf16(const void* a, const void* b, void* d, int m, int n, int k, int a_mn_major, int b_mn_major,
+                 int64_t lda, int64_t ldb, int64_t ldd, const void* bias_bf16, void* stream);
+
+/*
+ * Fake-quant linear, forward:  Y[T,N] = X[T,K] · qdq(W)ᵀ (+bias).  wq_scratch (bf16 [N,K]) receives the
+ * fake-quant weight once per call (reused by ar_fq_linear_bwd_dx).  = WrapperLinear.forward,
+ * auto_round/wrapper.py:517-565.
+ */
+int ar_fq_linear_fwd(const ar_qspec* q, const void* x_bf16, int64_t t, const void* w_bf16, const float* v,
+                     const float* min_scale, const float* max_scale, const void* wmin_bf16,
+                     const void* wmax_bf16, const float* gscale, const void* bias_bf16, void* wq_scratch,
+                     void* y_bf16, void* stream);
+/* dX[T,K] = dY[T,N] · Wq[N,K] */
+int ar_fq_linear_bwd_dx(const ar_qspec* q, const void* dy_bf16, int64_t t, const void* wq_bf16, void* dx_bf16,
+                        void* stream);
+/*
+ * dWq[N,K] = dYᵀ·X on tcgen05 with the qdq backward fused in the epilogue: the fp32 accumulator tile goes
+ * TMEM -> registers -> (dv, dmin, dmax) without ever materialising dWq.  Outputs are the PRE-sign
+ * gradients (sign is taken after the cross-GPU all-reduce, auto_round/.../sign_sgd.py:389).
+ * accumulate != 0 adds into dv/dmin/dmax (micro-batches / gradient_accumulate_steps).
+ */
+int ar_fq_linear_bwd_dw(const ar_qspec* q, const void* dy_bf16, const void* x_bf16, int64_t t, const void* w_bf16,
+                        const float* v, const float* min_scale, const float* max_scale, const void* wmin_bf16,
+                        const void* wmax_bf16, const float* gscale, float* dv, float* dmin, float* dmax,
+                        int accumulate, void* stream);
+
+/*
+ * Masked MSE + its gradient in one pass (auto_round/.../sign_round/quantizer.py:127-158, :789-803):
+ *   *loss_sum += sum(((pred*m) - (ref*m))^2)                       (double, UNnormalised, atomically accumulated)
+ *   dpred = bf16( ((2*inv_numel) * ((pred*m) - (ref*m))) * upstream ) * m      upstream = 1000 (loss*1000).backward()
+ * pred/ref bf16 [rows, cols]; row_mask (uint8 [rows], 1 = valid token) may be NULL; dpred may be NULL.
+ */
+int ar_mse_fwd_bwd(const void* pred_bf16, const void* ref_bf16, const uint8_t* row_mask, int64_t rows, int64_t cols,
+                   float inv_numel, float upstream, double* loss_sum, void* dpred_bf16, void* stream);
+
+/*
+ * Best-iteration bookkeeping on the device (no host sync in the loop; quantizer.py:477-515):
+ *   mean = fp32(*loss_sum * inv_numel); total = mean * inv_num_elm  (= loss.item()/num_elm)
+ *   state[0]=best_loss state[1]=last_loss state[2]=best_iter;  *flag = (total < best_loss);  loss_hist[iter]=total
+ *   *loss_sum is reset to 0 for the next iteration.  iter==0 initialises best_loss to FLT_MAX.
+ */
+int ar_best_update(double* loss_sum, double inv_numel, double inv_num_elm, int iter, double* state, int32_t* flag,
+                   float* loss_hist, void* stream);
+
+/*
+ * Sign-SGD step over a flat fp32 arena [ V of all layers | min/max_scale of all layers ]
+ * (SignSGD.step, sign_sgd.py:356-389, + the [0,hi] clamp the next forward would apply to min/max_scale,
+ * wrapper.py:257-259):
+ *   if (*flag) best[i] = p[i];           (collect_best_params, compressors/utils.py:205-217: PRE-update values)
+ *   p[i] -= lr * sign(g[i]);  for i >= clamp_begin: p[i] = clamp(p[i], 0, clamp_hi)
+ * lr_table[2*iter] (rounding lr) / lr_table[2*iter+1] (minmax lr) are read on the device so the step can live in
+ * a CUDA graph.  numel and clamp_begin must be multiples of 4.
+ */
+int ar_signsgd_step(float* p, const float* g, float* best, const int32_t* flag, const float* lr_table, int iter,
+                    int64_t numel, int64_t clamp_begin, float clamp_hi, void* stream);
+
+/* Gather `count` sample rows of `row_elems` bf16 each: dst[i] = src[idx[i]]  (BlockForwardRunner._select_batch). */
+int ar_gather_rows(const void* src_bf16, const int32_t* idx, int count, int64_t row_elems, void* dst_bf16,
+                   void* stream);
+
+/*
+ * INT pack (GPTQ-compatible int32 words along K, stored transposed) -- replaces
+ *   auto_round_extension/torch/qlinear_torch_zp.py:93-150 (zp_minus_one=1, sym: zp_const = 2^(bits-1))
+ *   auto_round_extension/torch/qlinear_torch.py:110-168, :170-281 (zp_minus_one=0, zp tensor)
+ * in:  wq bf16 [N,K] (qdq weight), scale fp16 [N,G'] (G' = ceil(K/g)), zp fp32 [N,G'] or NULL (+zp_const)
+ * out: qweight i32 [K*bits/32, N]; qzeros i32 [G', N*bits/32]; scales_t fp16 [G', N]; g_idx i32 [K]
+ */
+int ar_pack_int(const void* wq_bf16, const void* scale_f16, const float* zp, int zp_const, int n, int k, int bits,
+                int group_size, int zp_minus_one, int32_t* qweight, int32_t* qzeros, void* scales_t_f16,
+                int32_t* g_idx, void* stream);
+/* inverse (tests / round trips): W'[N,K] bf16 = (code - zp) * scale, as triton_utils/dequant.py:54-117 */
+int ar_unpack_int(const int32_t* qweight, const int32_t* qzeros, const void* scales_t_f16, int n, int k, int bits,
+                  int group_size, int zp_minus_one, void* w_bf16, int32_t* codes_or_null, void* stream);
+
+/*
+ * FP4 pack -- auto_round/export/export_to_autoround/qlinear_fp.py:141-193, :235-265
+ * nv: weight_packed u8 [N,K/2], weight_scale e4m3 bytes [N,K/16]; scale_f32 = layer.scale, gscale device scalar
+ * mx: weight_packed u8 [N,K/2], weight_scale u8 [N,K/32] = clamp(e+127,0,255); exp_bf16 = layer.scale
+ */
+int ar_pack_fp4_nv(const void* wq_bf16, const float* scale_f32, const float* gscale, int n, int k,
+                   uint8_t* weight_packed, uint8_t* weight_scale_e4m3, void* stream);
+int ar_pack_fp4_mx(const void* wq_bf16, const void* exp_bf16, int n, int k, uint8_t* weight_packed,
+                   uint8_t* weight_scale_e8m0, void* stream);
+int ar_unpack_fp4(const uint8_t* weight_packed, int n, int k, void* values_bf16, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AR_B200_H_ */
