@@ -1,0 +1,431 @@
+"""`AutoRound(...)` entry point -- keeps the reference's Python surface for the block-wise tuning path
+(auto_round/autoround.py:722-788; compressors/base.py:202-486, :1925-2021; compressors/orchestrator.py:176-388,
+:525-816; algorithms/composer.py:360-483) while every kernel of the hot path is hand-written sm_100a CUDA.
+
+    ar = AutoRound(model, tokenizer, scheme="W4A16", iters=200, nsamples=128, seqlen=2048, batch_size=8,
+                   dataset=[LongTensor[b, seqlen], ...], device_map=0, seed=42)
+    model, layer_config = ar.quantize()
+    ar.quantize_and_save("out_dir", format="auto_round")
+
+Out of scope (rejected loudly, never silently emulated): activation quantisation, GGUF / AWQ / MLX formats,
+AutoScheme, MLLM / diffusion calibration, torch.compile, CPU execution.
+"""
+from __future__ import annotations
+
+import random
+import time
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import export, ops
+from .quantizer import DataParallel, SignRoundQuantizer
+from .schemes import QuantizationScheme, parse_scheme
+from .wrapper import set_module
+
+_SCHEME_KW = ("bits", "group_size", "sym", "data_type", "act_bits", "act_group_size", "act_sym", "act_data_type",
+              "act_dynamic", "super_bits", "super_group_size")
+_SIGNROUND_KW = ("lr", "minmax_lr", "enable_minmax_tuning", "enable_quanted_input", "not_use_best_mse",
+                 "enable_norm_bias_tuning", "dynamic_max_gap", "momentum", "enable_alg_ext", "disable_opt_rtn",
+                 "enable_lfq", "nblocks", "quant_lm_head", "scale_dtype", "amp", "to_quant_block_names",
+                 "reference_mask_cast")
+
+
+class _StopForward(Exception):
+    pass
+
+
+def set_seed(seed: int):
+    """transformers.set_seed (compressors/base.py:360): python random, numpy, torch."""
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
+def find_blocks(model: nn.Module):
+    """utils/model.py:1380 get_block_names: the first ModuleList of decoder layers -> (prefix, ModuleList)."""
+    for name, mod in model.named_modules():
+        if isinstance(mod, nn.ModuleList) and len(mod) > 0 and all(isinstance(m, nn.Module) for m in mod):
+            if any(isinstance(sub, nn.Linear) for sub in mod[0].modules()):
+                return name, mod
+    raise RuntimeError("no transformer block list found in the model")
+
+
+class _GemmLinear(nn.Module):
+    """nn.Linear forward on the tcgen05 GEMM (used for the no-grad full-set block forwards)."""
+
+    def __init__(self, lin: nn.Linear):
+        super().__init__()
+        self.lin = lin
+
+    def forward(self, x):
+        w = self.lin.weight
+        x2d = x.reshape(-1, w.shape[1]).to(torch.bfloat16).contiguous()
+        b = None if self.lin.bias is None else self.lin.bias.to(torch.bfloat16).contiguous()
+        y = ops.gemm(x2d, w.contiguous(), bias=b)
+        return y.view(*x.shape[:-1], w.shape[0])
+
+
+class _swap_linears:
+    """Context manager: route every bf16 nn.Linear of a block through ops.gemm, then restore."""
+
+    def __init__(self, block: nn.Module):
+        self.block = block
+        self.saved = []
+
+    def __enter__(self):
+        for name, m in list(self.block.named_modules()):
+            if type(m) is nn.Linear and m.weight.is_cuda and m.weight.dtype == torch.bfloat16 \
+                    and m.weight.shape[1] % 8 == 0 and m.weight.shape[0] % 8 == 0:
+                self.saved.append((name, m))
+                set_module(self.block, name, _GemmLinear(m))
+        return self
+
+    def __exit__(self, *a):
+        for name, m in self.saved:
+            set_module(self.block, name, m)
+        return False
+
+
+class AutoRound:
+    def __init__(self, model, tokenizer=None, platform: str = "hf", scheme="W4A16", layer_config: Optional[dict] = None,
+                 dataset=None, iters: Optional[int] = None, seqlen: int = 2048, nsamples: int = 128, batch_size: int = 8,
+                 gradient_accumulate_steps: Optional[int] = None, low_gpu_mem_usage: bool = False, device_map=0,
+                 enable_torch_compile: Optional[bool] = None, seed: int = 42, low_cpu_mem_usage: bool = True,
+                 alg_configs=None, algorithm=None, **kwargs):
+        if isinstance(model, str):
+            from transformers import AutoModelForCausalLM, AutoTokenizer
+            tokenizer = tokenizer or AutoTokenizer.from_pretrained(model)
+            model = AutoModelForCausalLM.from_pretrained(model, torch_dtype="auto")
+        if not isinstance(model, nn.Module):
+            raise TypeError("model must be an nn.Module or a checkpoint path")
+        if tokenizer is None:
+            raise ValueError("a tokenizer object is required when `model` is a module (context/model.py:270-271)")
+        if platform != "hf":
+            raise NotImplementedError("only platform='hf'")
+        if algorithm not in (None, "signround") or alg_configs is not None:
+            raise NotImplementedError("only the default SignRound algorithm is built on B200")
+        if enable_torch_compile:
+            raise NotImplementedError("torch.compile is not part of the B200 path (hand-written kernels instead)")
+        unknown = set(kwargs) - set(_SCHEME_KW) - set(_SIGNROUND_KW)
+        if unknown:
+            raise TypeError(f"unsupported AutoRound arguments for the B200 hot path: {sorted(unknown)}")
+        for k in ("enable_norm_bias_tuning", "enable_lfq", "quant_lm_head"):
+            if kwargs.get(k):
+                raise NotImplementedError(f"{k}=True is outside the B200 hot path")
+        if kwargs.get("dynamic_max_gap", -1) not in (-1, None) or kwargs.get("momentum") not in (None, 0, 0.0):
+            raise NotImplementedError("dynamic_max_gap / momentum: only the reference defaults (-1 / 0)")
+        if kwargs.get("nblocks", 1) != 1:
+            raise NotImplementedError("nblocks != 1")
+        self.model = model.eval()
+        self.tokenizer = tokenizer
+        self.scheme: QuantizationScheme = parse_scheme(scheme, {k: kwargs.get(k) for k in _SCHEME_KW})
+        if kwargs.get("enable_alg_ext") and self.scheme.qdq_name != "int_asym":
+            raise NotImplementedError("enable_alg_ext: only the int-asym case (where the reference keeps the plain "
+                                      "WrapperLinear, sign_roundv2/quantizer.py:334-357) is in scope this round")
+        self.layer_config = layer_config or {}
+        self.dataset = dataset
+        self.iters = 200 if iters is None else int(iters)
+        self.seqlen, self.nsamples = int(seqlen), int(nsamples)
+        self.batch_size = min(int(batch_size), self.nsamples)            # compressors/base.py:234-241
+        self.gradient_accumulate_steps = gradient_accumulate_steps or 1
+        self.low_gpu_mem_usage = low_gpu_mem_usage
+        self.seed = seed
+        self.sign_kw = {k: kwargs[k] for k in ("lr", "minmax_lr", "enable_minmax_tuning", "enable_quanted_input",
+                                               "not_use_best_mse") if k in kwargs and kwargs[k] is not None}
+        # The reference casts EVERY cached non-integer block kwarg to the amp dtype (calibration/inputs.py:96-107,
+        # utils/model.py:1972-2000).  Under transformers >= 5 the 4-D attention mask is boolean, so that cast turns it
+        # into an additive +1/0 bias (future tokens become visible).  Default: keep the boolean mask (intended causal
+        # semantics, and it enables the is_causal attention path); reference_mask_cast=True reproduces the reference
+        # bit-for-bit for parity runs.
+        self.reference_mask_cast = bool(kwargs.get("reference_mask_cast", False))
+        self.device = self._resolve_device(device_map)
+        self.amp_dtype = torch.bfloat16
+        self.dp = self._resolve_dp()
+        set_seed(seed)
+        self.quantized = False
+        self.block_results = []
+        self.timings = {}
+        self._pack_on_the_fly = False
+        self._packed = False
+
+    # -------------------------------------------------------------------------------------------
+    @staticmethod
+    def _resolve_device(device_map):
+        if isinstance(device_map, torch.device):
+            dev = device_map
+        elif isinstance(device_map, int):
+            dev = torch.device("cuda", device_map)
+        elif isinstance(device_map, str):
+            s = device_map.strip()
+            if s in ("auto", "cuda"):
+                dev = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+            elif s.isdigit():
+                dev = torch.device("cuda", int(s))
+            else:
+                dev = torch.device(s)
+        else:
+            raise TypeError(f"device_map {device_map!r} not supported (one GPU per process; use torchrun for DP)")
+        if dev.type != "cuda":
+            raise RuntimeError("auto_round_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        return dev
+
+    @staticmethod
+    def _resolve_dp() -> DataParallel:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return DataParallel(dist.get_rank(), dist.get_world_size(), None)
+        return DataParallel()
+
+    # ------------------------------------------------------------------------------ calibration
+    def _token_batches(self):
+        """dataset = list of LongTensor [b, seqlen] (calibration/llm.py:305-317)."""
+        ds = self.dataset
+        if ds is None or isinstance(ds, str):
+            raise NotImplementedError("pass `dataset` as a list of token tensors [b, seqlen]; hub datasets need network")
+        if isinstance(ds, torch.Tensor):
+            ds = [ds]
+        total = 0
+        for data in ds:
+            if not isinstance(data, torch.Tensor):
+                raise TypeError("dataset entries must be LongTensor [b, seqlen]")
+            if data.dim() == 1:
+                data = data.unsqueeze(0)
+            if data.shape[-1] < self.seqlen:
+                continue
+            data = data[:, :self.seqlen]
+            if total + data.shape[0] > self.nsamples:
+                data = data[: self.nsamples - total]
+            if data.shape[0] == 0:
+                break
+            total += data.shape[0]
+            yield data
+            if total >= self.nsamples:
+                break
+
+    @torch.no_grad()
+    def cache_block_inputs(self, first_block: nn.Module):
+        """LLMCalibrator.calib (calibration/llm.py:283-451): run the token batches through the model, capture the
+        first block's inputs per sample and stop.  Reproduces the reference's mask conventions for tensor datasets:
+        last key masked, trailing repeated tokens masked, and -100 at every position excluded from the loss."""
+        model, dev = self.model, self.device
+        captured = {"hidden": [], "kwargs": None, "per_sample": {}}
+        shared = ("position_ids", "cache_position", "position_embeddings", "cu_seqlens")
+
+        def hook(mod, args, kwargs):
+            hs = args[0] if args else kwargs.get("hidden_states")
+            captured["hidden"].extend(torch.split(hs.detach(), 1, dim=0))
+            kw = {k: v for k, v in kwargs.items() if k != "hidden_states"}
+            if captured["kwargs"] is None:
+                captured["kwargs"] = {}
+                for k, v in kw.items():
+                    if k in shared or not isinstance(v, torch.Tensor):
+                        captured["kwargs"][k] = v
+            for k, v in kw.items():
+                if isinstance(v, torch.Tensor) and k not in shared:
+                    captured["per_sample"].setdefault(k, []).extend(torch.split(v.detach(), 1, dim=0))
+            raise _StopForward
+
+        # only what runs before the first block needs the device: everything except the other blocks
+        _, blocks = find_blocks(model)
+        moved = []
+        for name, mod in model.named_children():
+            moved.append(mod)
+        block_ids = {id(b) for b in blocks}
+        for mod in model.modules():
+            if id(mod) in block_ids:
+                continue
+            for p in mod.parameters(recurse=False):
+                p.data = p.data.to(dev)
+            for bname, b in mod.named_buffers(recurse=False):
+                mod._buffers[bname] = b.to(dev)
+        first_block.to(dev)
+        handle = first_block.register_forward_pre_hook(hook, with_kwargs=True)
+        ids_cache = []
+        try:
+            for data in self._token_batches():
+                input_ids = data.to(dev)
+                ids = input_ids.clone()
+                pad_id = getattr(self.tokenizer, "pad_token_id", None)
+                if pad_id is not None:
+                    ids[ids == pad_id] = -100
+                else:
+                    for b in range(ids.shape[0]):
+                        last = ids[b, -1].clone()
+                        j = ids.shape[1] - 2
+                        while j >= 0 and ids[b, j] == last:
+                            ids[b, j] = -100
+                            j -= 1
+                ids[:, -1] = -100
+                ids_cache.extend(torch.split(ids.cpu(), 1, dim=0))
+                if pad_id is not None and getattr(self.tokenizer, "pad_token", None) is not None:
+                    am = (input_ids != pad_id).to(torch.long)
+                else:
+                    am = torch.ones_like(input_ids, dtype=torch.long)
+                    for b in range(input_ids.shape[0]):
+                        last = input_ids[b, -1]
+                        j = input_ids.shape[1] - 2
+                        rep = False
+                        while j >= 0 and input_ids[b, j] == last:
+                            rep = True
+                            am[b, j] = 0
+                            j -= 1
+                        if rep:
+                            am[b, -1] = 0
+                am[:, -1] = 0
+                try:
+                    with torch.autocast(device_type="cuda", dtype=self.amp_dtype):
+                        model(input_ids, attention_mask=am, use_cache=False)
+                except _StopForward:
+                    pass
+        finally:
+            handle.remove()
+        others = dict(captured["kwargs"] or {})
+        for k, v in captured["per_sample"].items():
+            if self.reference_mask_cast:
+                v = [t if t.dtype in (torch.int32, torch.int64) else t.to(self.amp_dtype) for t in v]
+            others[k] = v
+        hidden = [h.to(self.amp_dtype) for h in captured["hidden"]]       # calibration/inputs.py:88-92
+        if len(hidden) == 0:
+            raise RuntimeError("no calibration samples: dataset sequences shorter than seqlen?")
+        return hidden, others, ids_cache
+
+    # ----------------------------------------------------------------------------------- forwards
+    @torch.no_grad()
+    def _forward_all(self, quantizer: SignRoundQuantizer, block, inputs, others, token_masks):
+        """BlockForwardRunner.forward over every sample in batches of `batch_size` (algorithms/block_runner.py:171)."""
+        dev = self.device
+        static_kw, per_sample_kw = quantizer._prepare_others(others, token_masks, dev)
+        outs = []
+        bs = self.batch_size
+        with _swap_linears(block):
+            for i in range(0, len(inputs), bs):
+                x = torch.cat([t.to(dev) for t in inputs[i:i + bs]], dim=0)
+                kw = dict(static_kw)
+                for k, v in per_sample_kw.items():
+                    kw[k] = v[i:i + bs]
+                y = quantizer.block_forward(block, x, kw)
+                outs.extend(torch.split(y.to(self.amp_dtype), 1, dim=0))
+        return outs
+
+    @staticmethod
+    def _fuse_nv_global_scales(block: nn.Module, names) -> dict:
+        """NVFP4: q/k/v and gate/up (w1/w3) share min(global_scale) (data_type/utils.py:433-530)."""
+        gs = {}
+        lin = {n: block.get_submodule(n) for n in names}
+        for n, m in lin.items():
+            gs[n] = ops.nv_global_scale(m.weight.data.contiguous())
+        groups = [("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj"), ("w1", "w3")]
+        by_parent = {}
+        for n in names:
+            parent, _, leaf = n.rpartition(".")
+            by_parent.setdefault(parent, {})[leaf] = n
+        for parent, leaves in by_parent.items():
+            for grp in groups:
+                members = [leaves[g] for g in grp if g in leaves]
+                if len(members) >= 2:
+                    shared = torch.stack([gs[m] for m in members]).min(dim=0).values
+                    for m in members:
+                        gs[m] = shared.clone()
+        return gs
+
+    def _hook(self, bi: int, phase: str):
+        cb = getattr(self, "block_hook", None)
+        if cb is not None:
+            cb(bi, phase)
+
+    # ---------------------------------------------------------------------------------- quantize
+    def quantize(self):
+        model = self.model
+        prefix, blocks = find_blocks(model)
+        t_cache0 = time.time()
+        fp_inputs, others, ids_cache = self.cache_block_inputs(blocks[0])
+        torch.cuda.synchronize(self.device)
+        self.timings["cache_inputs_s"] = time.time() - t_cache0
+        token_masks_cpu = [(ids != -100).reshape(-1) for ids in ids_cache]
+        any_masked = not all(bool(m.all()) for m in token_masks_cpu)
+        token_masks = [m.to(self.device) for m in token_masks_cpu] if any_masked else None
+
+        quantizer = SignRoundQuantizer(self.scheme, iters=self.iters, batch_size=self.batch_size, amp_dtype=self.amp_dtype,
+                                       layer_config=self.layer_config, dp=self.dp, **self.sign_kw)
+        self.quantizer = quantizer
+        t0 = time.time()                                                  # orchestrator.py:631
+        q_inputs = None
+        nblk = len(blocks)
+        for bi, block in enumerate(blocks):
+            tb = time.time()
+            self._hook(bi, "h2d0")
+            block.to(self.device)                                         # H2D of this block's weights
+            for p in block.parameters():
+                p.requires_grad_(False)
+                if p.dtype in (torch.float32, torch.float16):
+                    p.data = p.data.to(self.amp_dtype)
+            self._hook(bi, "compute0")
+            names = [n for n, m in block.named_modules() if quantizer.layer_filter(n, m)
+                     and (quantizer.scheme_for(n, m) is not None) and quantizer.scheme_for(n, m).bits <= 8]
+            # (3) reference outputs of the FP block on the FP inputs  (composer.py:423-429)
+            ref_out = self._forward_all(quantizer, block, fp_inputs, others, token_masks)
+            nv_gs = self._fuse_nv_global_scales(block, names) if self.scheme.qdq_name == "nv_fp4" else None
+            eff = q_inputs if (q_inputs is not None and quantizer.enable_quanted_input) else fp_inputs
+            quantizer.quantize_block(block, eff, others, ref_out, q_inputs, None, input_ids=ids_cache,
+                                     nv_global_scales=nv_gs)
+            res = quantizer.last_result
+            # (6) outputs of the quantised block feed the next block (composer.py:476-481)
+            if quantizer.enable_quanted_input and bi + 1 < nblk:
+                q_inputs = self._forward_all(quantizer, block, eff, others, token_masks)
+            else:
+                q_inputs = None
+            fp_inputs = ref_out
+            if self._pack_on_the_fly:                                     # immediate_pack (orchestrator.py:327-337)
+                for n in res.quantized_layers:
+                    export.pack_layer(n, block, quantizer.scheme_for(n, block.get_submodule(n)), self.device,
+                                      out_device=self.device)
+            self._hook(bi, "d2h0")
+            block.to("cpu")                                               # packed tensors (or qdq weights) -> host
+            self._hook(bi, "done")
+            torch.cuda.synchronize(self.device)
+            self.block_results.append({"block": f"{prefix}.{bi}", "init_loss": res.init_loss, "best_loss": res.best_loss,
+                                       "best_iter": res.best_iter, "seconds": time.time() - tb, "losses": res.losses})
+        self.timings["tuning_s"] = time.time() - t0                      # "quantization tuning time" (orchestrator.py:792)
+        self.quantized = True
+        self._packed = self._pack_on_the_fly
+        self.block_prefix = prefix
+        layer_cfg = {}
+        for bi, block in enumerate(blocks):
+            for n, m in block.named_modules():
+                if hasattr(m, "scale") or isinstance(m, export.QuantLinear):
+                    layer_cfg[f"{prefix}.{bi}.{n}"] = self.scheme.to_dict()
+        self.layer_config_out = layer_cfg
+        return model, layer_cfg
+
+    def save_quantized(self, output_dir: Optional[str] = None, format: str = "auto_round", inplace: bool = True):
+        if format not in ("auto_round", "auto_round:auto_gptq"):
+            raise NotImplementedError(f"format {format!r}: only the auto_round checkpoint format is in scope")
+        if not self.quantized:
+            raise RuntimeError("call quantize() first")
+        prefix, blocks = find_blocks(self.model)
+        if not self._packed:
+            for block in blocks:
+                for n, m in list(block.named_modules()):
+                    if type(m) is nn.Linear and hasattr(m, "scale"):
+                        export.pack_layer(n, block, self.quantizer.scheme_for(n, m), self.device)
+            self._packed = True
+        qcfg = export.build_quantization_config(self.scheme, prefix, None, self.iters, self.nsamples, self.seqlen,
+                                                self.batch_size)
+        self.quantization_config = qcfg
+        if output_dir is None:
+            self.model.config.quantization_config = qcfg
+            return self.model
+        export.save_quantized(self.model, output_dir, qcfg, self.tokenizer)
+        return self.model
+
+    def quantize_and_save(self, output_dir: str = "tmp_autoround", format: Optional[str] = None, inplace: bool = True):
+        fmt = format or "auto_round"
+        self._pack_on_the_fly = True
+        model, _ = self.quantize()
+        self.save_quantized(output_dir, fmt, inplace)
+        return model, [output_dir]

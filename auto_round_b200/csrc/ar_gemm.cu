@@ -219,9 +219,10 @@ __device__ __forceinline__ void epilogue_dw(const GemmParams& p, uint32_t tmem_a
   for (int c = 0; c < BN / 32; ++c) {
     const int k0 = col0 + c * 32;
     uint32_t r[32];
+    __syncwarp();                                  // tcgen05.ld is .sync.aligned: reconverge the warp first
     tmem_ld32(tmem_acc + (uint32_t)(c * 32), r);   // warp-collective: every lane executes it
     tmem_ld_wait();
-    if (!row_ok || k0 >= K) continue;
+    if (!row_ok || k0 >= K) continue;              // (lanes of a tail tile idle; they rejoin at __syncwarp)
     const int64_t off = (int64_t)row * K + k0;
     float w[32], v[32];
 #pragma unroll

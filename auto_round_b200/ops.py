@@ -13,6 +13,19 @@ import torch
 from . import _lib
 from ._lib import DT_INT_ASYM, DT_INT_SYM, DT_MX_FP4, DT_NV_FP4, QSpec
 
+# number of kernels of libar_b200.so launched through this module (bench.py reports it as `gpu_launches`)
+LAUNCHES = [0]
+_KERNELS_PER_CALL = {"ar_group_minmax": 1, "ar_absmax": 1, "ar_nv_global_scale": 1, "ar_qdq_fwd": 1, "ar_qdq_bwd": 1,
+                     "ar_gemm_bf16": 1, "ar_fq_linear_fwd": 2, "ar_fq_linear_bwd_dx": 1, "ar_fq_linear_bwd_dw": 1,
+                     "ar_mse_fwd_bwd": 1, "ar_best_update": 1, "ar_signsgd_step": 1, "ar_gather_rows": 1,
+                     "ar_pack_int": 3, "ar_unpack_int": 1, "ar_pack_fp4_nv": 1, "ar_pack_fp4_mx": 1, "ar_unpack_fp4": 1}
+
+
+def _check(rc, what):
+    LAUNCHES[0] += _KERNELS_PER_CALL.get(what, 1)
+    _lib.check(rc, what)
+
+
 DTYPE_IDS = {"int_sym": DT_INT_SYM, "int_asym": DT_INT_ASYM, "mx_fp4": DT_MX_FP4, "nv_fp4": DT_NV_FP4}
 
 
@@ -74,7 +87,7 @@ def group_minmax(spec: Spec, w: torch.Tensor):
     wmin = torch.empty(spec.groups, dtype=torch.bfloat16, device=w.device)
     wmax = torch.empty_like(wmin)
     cs = spec.c()
-    _lib.check(_lib.load().ar_group_minmax(C.byref(cs), _p(w), _p(wmin), _p(wmax), _stream()), "ar_group_minmax")
+    _check(_lib.load().ar_group_minmax(C.byref(cs), _p(w), _p(wmin), _p(wmax), _stream()), "ar_group_minmax")
     return wmin, wmax
 
 
@@ -84,8 +97,8 @@ def nv_global_scale(w: torch.Tensor) -> torch.Tensor:
     amax = torch.zeros(1, dtype=torch.float32, device=w.device)
     gs = torch.empty(1, dtype=torch.float32, device=w.device)
     lib = _lib.load()
-    _lib.check(lib.ar_absmax(_p(w), w.numel(), _p(amax), _stream()), "ar_absmax")
-    _lib.check(lib.ar_nv_global_scale(_p(amax), _p(gs), _stream()), "ar_nv_global_scale")
+    _check(lib.ar_absmax(_p(w), w.numel(), _p(amax), _stream()), "ar_absmax")
+    _check(lib.ar_nv_global_scale(_p(amax), _p(gs), _stream()), "ar_nv_global_scale")
     return gs
 
 
@@ -104,7 +117,7 @@ def qdq_fwd(spec: Spec, w, v=None, min_scale=None, max_scale=None, wmin=None, wm
     scale = torch.empty(spec.groups, dtype=scale_dtype_of(spec), device=w.device) if want_scale else None
     zp = torch.empty(spec.groups, dtype=torch.float32, device=w.device) if (want_scale and spec.dtype == DT_INT_ASYM) else None
     cs = spec.c()
-    _lib.check(_lib.load().ar_qdq_fwd(C.byref(cs), _p(w), _p(v), _p(min_scale), _p(max_scale), _p(wmin), _p(wmax),
+    _check(_lib.load().ar_qdq_fwd(C.byref(cs), _p(w), _p(v), _p(min_scale), _p(max_scale), _p(wmin), _p(wmax),
                                       _p(gscale), _p(wq), _p(scale), _p(zp), _stream()), "ar_qdq_fwd")
     return wq, scale, zp
 
@@ -122,7 +135,7 @@ def qdq_bwd(spec: Spec, w, gq, v=None, min_scale=None, max_scale=None, wmin=None
     if dmin is None and spec.is_int:
         dmin = torch.empty(spec.groups, dtype=torch.float32, device=dev)
     cs = spec.c()
-    _lib.check(_lib.load().ar_qdq_bwd(C.byref(cs), _p(w), _p(v), _p(min_scale), _p(max_scale), _p(wmin), _p(wmax),
+    _check(_lib.load().ar_qdq_bwd(C.byref(cs), _p(w), _p(v), _p(min_scale), _p(max_scale), _p(wmin), _p(wmax),
                                       _p(gscale), _p(gq), _p(dv), _p(dmin), _p(dmax), int(accumulate), _stream()),
                "ar_qdq_bwd")
     return dv, dmin, dmax
@@ -143,7 +156,7 @@ def gemm(a, b, a_mn_major=False, b_mn_major=False, bias=None, out=None):
     if kb != k:
         raise ValueError(f"reduction dims differ: {k} vs {kb}")
     d = out if out is not None else torch.empty(m, n, dtype=torch.bfloat16, device=a.device)
-    _lib.check(_lib.load().ar_gemm_bf16(_p(a), _p(b), _p(d), m, n, k, int(a_mn_major), int(b_mn_major),
+    _check(_lib.load().ar_gemm_bf16(_p(a), _p(b), _p(d), m, n, k, int(a_mn_major), int(b_mn_major),
                                         a.stride(0), b.stride(0), d.stride(0), _p(bias), _stream()), "ar_gemm_bf16")
     return d
 
@@ -153,7 +166,7 @@ def fq_linear_fwd(spec: Spec, x2d, w, v, min_scale, max_scale, wmin, wmax, gscal
     t = x2d.shape[0]
     y = out if out is not None else torch.empty(t, spec.n, dtype=torch.bfloat16, device=x2d.device)
     cs = spec.c()
-    _lib.check(_lib.load().ar_fq_linear_fwd(C.byref(cs), _p(x2d), t, _p(w), _p(v), _p(min_scale), _p(max_scale), _p(wmin),
+    _check(_lib.load().ar_fq_linear_fwd(C.byref(cs), _p(x2d), t, _p(w), _p(v), _p(min_scale), _p(max_scale), _p(wmin),
                                             _p(wmax), _p(gscale), _p(bias), _p(wq_scratch), _p(y), _stream()),
                "ar_fq_linear_fwd")
     return y
@@ -164,7 +177,7 @@ def fq_linear_bwd_dx(spec: Spec, dy2d, wq, out=None):
     t = dy2d.shape[0]
     dx = out if out is not None else torch.empty(t, spec.k, dtype=torch.bfloat16, device=dy2d.device)
     cs = spec.c()
-    _lib.check(_lib.load().ar_fq_linear_bwd_dx(C.byref(cs), _p(dy2d), t, _p(wq), _p(dx), _stream()), "ar_fq_linear_bwd_dx")
+    _check(_lib.load().ar_fq_linear_bwd_dx(C.byref(cs), _p(dy2d), t, _p(wq), _p(dx), _stream()), "ar_fq_linear_bwd_dx")
     return dx
 
 
@@ -173,7 +186,7 @@ def fq_linear_bwd_dw(spec: Spec, dy2d, x2d, w, v, min_scale, max_scale, wmin, wm
     _want(dy2d, torch.bfloat16, "dy")
     _want(x2d, torch.bfloat16, "x")
     cs = spec.c()
-    _lib.check(_lib.load().ar_fq_linear_bwd_dw(C.byref(cs), _p(dy2d), _p(x2d), dy2d.shape[0], _p(w), _p(v), _p(min_scale),
+    _check(_lib.load().ar_fq_linear_bwd_dw(C.byref(cs), _p(dy2d), _p(x2d), dy2d.shape[0], _p(w), _p(v), _p(min_scale),
                                                _p(max_scale), _p(wmin), _p(wmax), _p(gscale), _p(dv), _p(dmin), _p(dmax),
                                                int(accumulate), _stream()), "ar_fq_linear_bwd_dw")
 
@@ -187,20 +200,20 @@ def mse_fwd_bwd(pred2d, ref2d, row_mask, inv_numel, upstream, loss_sum, dpred=No
     rows, cols = pred2d.shape
     if want_grad and dpred is None:
         dpred = torch.empty_like(pred2d)
-    _lib.check(_lib.load().ar_mse_fwd_bwd(_p(pred2d), _p(ref2d), _p(row_mask), rows, cols, float(inv_numel), float(upstream),
+    _check(_lib.load().ar_mse_fwd_bwd(_p(pred2d), _p(ref2d), _p(row_mask), rows, cols, float(inv_numel), float(upstream),
                                           _p(loss_sum), _p(dpred) if want_grad else None, _stream()), "ar_mse_fwd_bwd")
     return dpred
 
 
 def best_update(loss_sum, inv_numel, inv_num_elm, it, state, flag, loss_hist):
-    _lib.check(_lib.load().ar_best_update(_p(loss_sum), float(inv_numel), float(inv_num_elm), int(it), _p(state), _p(flag),
+    _check(_lib.load().ar_best_update(_p(loss_sum), float(inv_numel), float(inv_num_elm), int(it), _p(state), _p(flag),
                                           _p(loss_hist), _stream()), "ar_best_update")
 
 
 def signsgd_step(p, g, best, flag, lr_table, it, clamp_begin, clamp_hi=1.0):
     _want(p, torch.float32, "p")
     _want(g, torch.float32, "g")
-    _lib.check(_lib.load().ar_signsgd_step(_p(p), _p(g), _p(best), _p(flag), _p(lr_table), int(it), p.numel(),
+    _check(_lib.load().ar_signsgd_step(_p(p), _p(g), _p(best), _p(flag), _p(lr_table), int(it), p.numel(),
                                            int(clamp_begin), float(clamp_hi), _stream()), "ar_signsgd_step")
 
 
@@ -212,7 +225,7 @@ def gather_rows(src, idx_i32, out=None):
     row = src[0].numel()
     if out is None:
         out = torch.empty((count,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
-    _lib.check(_lib.load().ar_gather_rows(_p(src), _p(idx_i32), count, row, _p(out), _stream()), "ar_gather_rows")
+    _check(_lib.load().ar_gather_rows(_p(src), _p(idx_i32), count, row, _p(out), _stream()), "ar_gather_rows")
     return out
 
 
@@ -229,7 +242,7 @@ def pack_int(wq, scale_f16, zp, bits, group_size, zp_minus_one, zp_const=0):
     qzeros = torch.empty(ng, n * bits // 32, dtype=torch.int32, device=dev)
     scales_t = torch.empty(ng, n, dtype=torch.float16, device=dev)
     g_idx = torch.empty(k, dtype=torch.int32, device=dev)
-    _lib.check(_lib.load().ar_pack_int(_p(wq), _p(scale_f16), _p(zp), int(zp_const), n, k, bits, g, int(zp_minus_one),
+    _check(_lib.load().ar_pack_int(_p(wq), _p(scale_f16), _p(zp), int(zp_const), n, k, bits, g, int(zp_minus_one),
                                        _p(qweight), _p(qzeros), _p(scales_t), _p(g_idx), _stream()), "ar_pack_int")
     return qweight, qzeros, scales_t, g_idx
 
@@ -238,7 +251,7 @@ def unpack_int(qweight, qzeros, scales_t, n, k, bits, group_size, zp_minus_one, 
     g = k if group_size in (-1, 0) else group_size
     w = torch.empty(n, k, dtype=torch.bfloat16, device=qweight.device)
     codes = torch.empty(n, k, dtype=torch.int32, device=qweight.device) if want_codes else None
-    _lib.check(_lib.load().ar_unpack_int(_p(qweight), _p(qzeros), _p(scales_t), n, k, bits, g, int(zp_minus_one), _p(w),
+    _check(_lib.load().ar_unpack_int(_p(qweight), _p(qzeros), _p(scales_t), n, k, bits, g, int(zp_minus_one), _p(w),
                                          _p(codes), _stream()), "ar_unpack_int")
     return w, codes
 
@@ -249,7 +262,7 @@ def pack_fp4_nv(wq, scale_f32, gscale):
     n, k = wq.shape
     packed = torch.empty(n, k // 2, dtype=torch.uint8, device=wq.device)
     sc = torch.empty(n, k // 16, dtype=torch.uint8, device=wq.device)
-    _lib.check(_lib.load().ar_pack_fp4_nv(_p(wq), _p(scale_f32), _p(gscale), n, k, _p(packed), _p(sc), _stream()),
+    _check(_lib.load().ar_pack_fp4_nv(_p(wq), _p(scale_f32), _p(gscale), n, k, _p(packed), _p(sc), _stream()),
                "ar_pack_fp4_nv")
     return packed, sc
 
@@ -260,11 +273,11 @@ def pack_fp4_mx(wq, exp_bf16):
     n, k = wq.shape
     packed = torch.empty(n, k // 2, dtype=torch.uint8, device=wq.device)
     sc = torch.empty(n, k // 32, dtype=torch.uint8, device=wq.device)
-    _lib.check(_lib.load().ar_pack_fp4_mx(_p(wq), _p(exp_bf16), n, k, _p(packed), _p(sc), _stream()), "ar_pack_fp4_mx")
+    _check(_lib.load().ar_pack_fp4_mx(_p(wq), _p(exp_bf16), n, k, _p(packed), _p(sc), _stream()), "ar_pack_fp4_mx")
     return packed, sc
 
 
 def unpack_fp4(packed, n, k):
     out = torch.empty(n, k, dtype=torch.bfloat16, device=packed.device)
-    _lib.check(_lib.load().ar_unpack_fp4(_p(packed), n, k, _p(out), _stream()), "ar_unpack_fp4")
+    _check(_lib.load().ar_unpack_fp4(_p(packed), n, k, _p(out), _stream()), "ar_unpack_fp4")
     return out

@@ -1,0 +1,378 @@
+"""Block-wise SignRound tuning on B200 -- host-side mirror of
+auto_round/algorithms/quantization/sign_round/quantizer.py:311-552 (SignRoundQuantizer.quantize_block).
+
+Same call contract as the reference's plug point: `quantize_block(block, fp_inputs, input_others,
+fp_outputs, q_inputs, block_ctx, input_ids=None)` mutates `block` in place (qdq weights, `.scale/.zp/
+.weight_global_scale` attributes on every quantised nn.Linear) and returns the best parameters.
+
+What is different from the reference (B200-first):
+  * all tunables of a block live in ONE flat fp32 arena [V of every layer | scales of every layer] with a matching
+    gradient arena and best-snapshot arena, so the optimiser is one kernel and the data-parallel exchange is one
+    NCCL all-reduce per iteration;
+  * loss, best-iteration selection, snapshot and sign-SGD update run on the device without any host
+    synchronisation inside the 200-iteration loop (the reference calls loss.item() every iteration);
+  * the sampler's batch sequence is drawn up-front (same python `random` stream, compressors/utils.py:388-438) and
+    uploaded once; samples are gathered on the device;
+  * calibration samples shard across ranks (rank r takes batch[r::world]); gradients are summed BEFORE the sign.
+"""
+from __future__ import annotations
+
+import random
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .schemes import QuantizationScheme
+from .wrapper import WrapperLinear, set_module
+
+SHARED_CACHE_KEYS = ("position_ids", "cache_position", "position_embeddings", "cu_seqlens")  # utils/common.py:676
+
+
+class IndexSampler:
+    """auto_round/compressors/utils.py:388-438 -- cyclic shuffled batches from the GLOBAL python `random` state."""
+
+    def __init__(self, nsamples: int, batch_size: int):
+        if batch_size <= 0 or batch_size > nsamples:
+            raise ValueError("batch_size must be > 0 and <= nsamples")
+        self.nsamples, self.batch_size, self.index = nsamples, batch_size, 0
+        self.indices = list(range(nsamples))
+        random.shuffle(self.indices)
+
+    def next_batch(self):
+        if self.index + self.batch_size > self.nsamples:
+            random.shuffle(self.indices)
+            self.index = 0
+        batch = self.indices[self.index:self.index + self.batch_size]
+        self.index += self.batch_size
+        return batch
+
+
+def lr_schedule_table(iters: int, lr: float, minmax_lr: float) -> np.ndarray:
+    """LinearLR(start 1.0 -> end 0.0 over `iters`) applied to fp32 lr tensors, chainable form
+    (quantizer.py:426-429, torch.optim.lr_scheduler.LinearLR.get_lr): lr_{t+1} = fp32(lr_t * fp32(1 - 1/(iters-t))).
+    Returns [iters, 2] float32: column 0 rounding lr, column 1 minmax lr."""
+    tab = np.zeros((max(iters, 1), 2), dtype=np.float32)
+    a, b = np.float32(lr), np.float32(minmax_lr)
+    for t in range(iters):
+        tab[t, 0], tab[t, 1] = a, b
+        f = np.float32(1.0 + (0.0 - 1.0) / (iters * 1.0 + t * (0.0 - 1.0)))
+        a, b = np.float32(a * f), np.float32(b * f)
+    return tab
+
+
+class TuneArena:
+    """Flat fp32 storage for every tunable of one block: [ V_0 | V_1 | ... | scales ... ]."""
+
+    def __init__(self, specs: dict, device):
+        off = 0
+        self.views = {}
+        for name, spec in specs.items():
+            n = spec.n * spec.kpad
+            self.views[name] = {"value": (off, n, (spec.n, spec.kpad))}
+            off += n
+        self.clamp_begin = off                       # first scale parameter (multiple of 16: kpad % 16 == 0)
+        for name, spec in specs.items():
+            g = spec.groups
+            self.views[name]["max_scale"] = (off, g, (g,))
+            off += (g + 3) // 4 * 4
+            if spec.is_int:                           # mx/nv ignore min_scale (it never receives a gradient)
+                self.views[name]["min_scale"] = (off, g, (g,))
+                off += (g + 3) // 4 * 4
+        self.numel = off
+        self.params = torch.zeros(off, dtype=torch.float32, device=device)
+        self.params[self.clamp_begin:] = 1.0          # min/max_scale start at 1, V at 0 (wrapper.py:184-190)
+        self.grads = torch.zeros(off, dtype=torch.float32, device=device)
+        self.best = torch.zeros(off, dtype=torch.float32, device=device)
+
+    def layer_views(self, name: str) -> dict:
+        out = {}
+        for key, (o, n, shape) in self.views[name].items():
+            out[key] = self.params[o:o + n].view(shape)
+            out["grad_" + key] = self.grads[o:o + n].view(shape)
+        return out
+
+    def best_views(self, name: str) -> dict:
+        return {key: self.best[o:o + n].view(shape) for key, (o, n, shape) in self.views[name].items()}
+
+
+@dataclass
+class DataParallel:
+    """Calibration-sample sharding over the ranks of one NVSwitch box.  `group` may be a gloo
+    group in the CPU tests of the host logic."""
+    rank: int = 0
+    world: int = 1
+    group: object = None
+
+    def shard(self, batch):
+        return list(batch)[self.rank::self.world]
+
+    def all_reduce_(self, *tensors):
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        for t in tensors:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+
+@dataclass
+class TuneResult:
+    losses: list = field(default_factory=list)
+    best_iter: int = 0
+    best_loss: float = float("inf")
+    init_loss: float = float("nan")
+    batches: list = field(default_factory=list)
+    quantized_layers: list = field(default_factory=list)
+
+
+def default_layer_filter(name: str, module: nn.Module) -> bool:
+    return type(module) is nn.Linear
+
+
+def _causal_equivalent(masks, token_masks) -> bool:
+    """True if every cached attention mask is plain causal except, at most, entries in the LAST query row whose
+    token is excluded from the loss.  The reference builds exactly that mask for tensor datasets (last key masked,
+    calibration/llm.py:375-398; last position -100, :359-360), and the last row of a causal block influences no
+    other row, so the fast is_causal attention path is numerically identical on every row that matters."""
+    if masks is None:
+        return True
+    if token_masks is None:
+        return False
+    for m, tm in zip(masks, token_masks):
+        if m is None:
+            continue
+        if m.dim() != 4 or m.shape[-1] != m.shape[-2]:
+            return False
+        s = m.shape[-1]
+        allowed = (m != 0) if m.dtype == torch.bool else (m == 0)
+        causal = torch.ones(s, s, dtype=torch.bool, device=m.device).tril()
+        diff = (allowed.reshape(-1, s, s) != causal).any(-1).any(0)        # rows that differ
+        if bool(diff[:-1].any()):
+            return False
+        if bool(diff[-1]) and int(tm.reshape(-1)[-1]) != 0:
+            return False
+    return True
+
+
+class SignRoundQuantizer:
+    """Tuning loop driver.  Hyper-parameters follow SignRoundConfig (sign_round/config.py:21-178)."""
+
+    def __init__(self, scheme: QuantizationScheme, iters: int = 200, lr: Optional[float] = None,
+                 minmax_lr: Optional[float] = None, batch_size: int = 8, enable_minmax_tuning: bool = True,
+                 enable_quanted_input: bool = True, not_use_best_mse: bool = False, amp_dtype=torch.bfloat16,
+                 layer_config: Optional[dict] = None, layer_filter=default_layer_filter,
+                 dp: Optional[DataParallel] = None, gradient_accumulate_steps: int = 1):
+        self.scheme = scheme
+        self.iters = iters
+        self.lr_is_auto = lr is None
+        self.lr = lr
+        self.minmax_lr = minmax_lr
+        self.batch_size = batch_size
+        self.enable_minmax_tuning = enable_minmax_tuning
+        self.enable_quanted_input = enable_quanted_input
+        self.not_use_best_mse = not_use_best_mse
+        self.amp_dtype = amp_dtype
+        self.layer_config = layer_config or {}
+        self.layer_filter = layer_filter
+        self.dp = dp or DataParallel()
+        if gradient_accumulate_steps != 1:
+            raise NotImplementedError("gradient_accumulate_steps != 1 (reference default is 1)")
+        self.last_result: Optional[TuneResult] = None
+        self.last_arena = None
+
+    # sign_round/config.py:107-136
+    def compute_lr(self, bits: int) -> float:
+        if not self.lr_is_auto:
+            return float(self.lr)
+        if self.iters >= 1000 and bits <= 3:
+            return 2.0 / self.iters
+        return 1.0 / max(self.iters, 1)
+
+    def scheme_for(self, name: str, module: nn.Module) -> Optional[QuantizationScheme]:
+        cfg = self.layer_config.get(name)
+        if cfg is None:
+            g = getattr(module, "global_name", None)
+            cfg = self.layer_config.get(g) if g else None
+        if cfg is None:
+            return self.scheme
+        if isinstance(cfg, QuantizationScheme):
+            return cfg
+        from dataclasses import replace
+        s = replace(self.scheme)
+        for k, v in cfg.items():
+            if hasattr(s, k):
+                setattr(s, k, v)
+        return s
+
+    # ---------------------------------------------------------------------------------------------
+    def wrapper_block(self, block: nn.Module, nv_global_scales: Optional[dict] = None):
+        """wrapper.py:774-828: every eligible nn.Linear (bits <= 8) -> WrapperLinear on the block arena."""
+        todo = {}
+        for name, mod in block.named_modules():
+            if self.layer_filter(name, mod):
+                sc = self.scheme_for(name, mod)
+                if sc is None or sc.bits > 8:
+                    continue
+                n, k = mod.weight.shape
+                thr = 1e-5
+                todo[name] = (mod, sc, ops.make_spec(sc.qdq_name, sc.bits, sc.group_size, n, k, thr, 1.0))
+        if not todo:
+            return {}, None
+        device = next(iter(todo.values()))[0].weight.device
+        arena = TuneArena({n: t[2] for n, t in todo.items()}, device)
+        wrapped = {}
+        for name, (mod, sc, spec) in todo.items():
+            gs = None if nv_global_scales is None else nv_global_scales.get(name)
+            wl = WrapperLinear(mod, sc, spec, arena.layer_views(name), gs)
+            set_module(block, name, wl)
+            wrapped[name] = wl
+        return wrapped, arena
+
+    def unwrapper_block(self, block: nn.Module, wrapped: dict, arena: TuneArena, use_best: bool = True):
+        for name, wl in wrapped.items():
+            views = arena.best_views(name) if use_best else {k: v for k, v in wl.params.items()}
+            lin = wl.unwrapper(views)
+            set_module(block, name, lin)
+
+    # ---------------------------------------------------------------------------------------------
+    def _stack(self, samples, device):
+        if isinstance(samples, torch.Tensor):
+            return samples.to(device).contiguous()
+        t = torch.cat([s.to(device, non_blocking=True) for s in samples], dim=0)
+        return t.contiguous()
+
+    def _prepare_others(self, input_others: dict, token_masks, device):
+        """Split block kwargs into (static kwargs, per-sample stacked tensors); drop a causal-equivalent mask."""
+        static, per_sample = {}, {}
+        others = dict(input_others or {})
+        others.pop("positional_inputs", None)
+        am = others.get("attention_mask")
+        if isinstance(am, (list, tuple)) and len(am) and isinstance(am[0], torch.Tensor):
+            if _causal_equivalent(am, token_masks):
+                others["attention_mask"] = None          # -> is_causal fast path inside the HF attention
+        for key, val in others.items():
+            if key in SHARED_CACHE_KEYS:
+                v = val[0] if isinstance(val, (list, tuple)) and len(val) >= 1 and not isinstance(val[0], (int, float)) else val
+                static[key] = _to_device(v, device)
+            elif isinstance(val, (list, tuple)) and len(val) and isinstance(val[0], torch.Tensor):
+                per_sample[key] = torch.cat([v.to(device) for v in val], dim=0)
+            elif isinstance(val, torch.Tensor):
+                per_sample[key] = val.to(device)
+            else:
+                static[key] = val
+        return static, per_sample
+
+    def block_forward(self, block, x, kwargs):
+        """compressors/utils.py:109-172: HF decoder layer under autocast(amp dtype); first output."""
+        with torch.autocast(device_type="cuda", dtype=self.amp_dtype):
+            out = block(x, **kwargs)
+        return out[0] if isinstance(out, (tuple, list)) else out
+
+    # ---------------------------------------------------------------------------------------------
+    def quantize_block(self, block: nn.Module, fp_inputs, input_others, fp_outputs, q_inputs=None, block_ctx=None,
+                       input_ids=None, nv_global_scales: Optional[dict] = None, **kwargs) -> dict:
+        dp = self.dp
+        active = q_inputs if (q_inputs is not None and self.enable_quanted_input) else fp_inputs
+        device = next(block.parameters()).device
+        if device.type != "cuda":
+            raise RuntimeError("quantize_block: block must be on a CUDA device (auto_round_b200 has no CPU path)")
+        x_all = self._stack(active, device)
+        ref_all = self._stack(fp_outputs, device)
+        nsamples = x_all.shape[0]
+        seq, hidden = x_all.shape[1], x_all.shape[-1]
+
+        token_masks = None
+        if input_ids is not None:
+            masks = [(ids != -100).reshape(-1) for ids in input_ids]
+            if not all(bool(m.all()) for m in masks):                     # base.py:257-280
+                token_masks = torch.stack(masks).to(device=device, dtype=torch.uint8).contiguous()
+        valid_per_sample = None if token_masks is None else token_masks.sum(dim=1).cpu().tolist()
+
+        wrapped, arena = self.wrapper_block(block, nv_global_scales)
+        self.last_arena = arena if kwargs.get("keep_arena") else None
+        res = TuneResult(quantized_layers=list(wrapped))
+        self.last_result = res
+        if not wrapped or self.iters <= 0:
+            if wrapped:
+                arena.best.copy_(arena.params)
+                self.unwrapper_block(block, wrapped, arena)
+            return {}
+
+        static_kw, per_sample_kw = self._prepare_others(
+            input_others, None if token_masks is None else list(token_masks), device)
+
+        # ---- schedules drawn up-front (same python-random stream as the reference's IndexSampler)
+        iters = self.iters
+        gbs = min(nsamples, self.batch_size)
+        sampler = kwargs.get("sampler") or IndexSampler(nsamples, gbs)
+        batches = [list(sampler.next_batch()) for _ in range(iters)]
+        res.batches = batches
+        local = [dp.shard(b) for b in batches]
+        lbs = len(local[0])
+        if lbs == 0:
+            raise RuntimeError(f"batch_size {gbs} cannot be sharded over {dp.world} ranks")
+        idx_dev = torch.tensor(local, dtype=torch.int32, device=device)
+        bits_all = {wl.scheme.bits for wl in wrapped.values()}
+        lr0 = self.compute_lr(min(bits_all))
+        mm_lr0 = float(self.minmax_lr) if self.minmax_lr is not None else lr0
+        if not self.enable_minmax_tuning:
+            mm_lr0 = 0.0
+        lr_tab = torch.from_numpy(lr_schedule_table(iters, lr0, mm_lr0)).to(device).reshape(-1)
+
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=device)
+        state = torch.zeros(4, dtype=torch.float64, device=device)
+        flag = torch.zeros(1, dtype=torch.int32, device=device)
+        hist = torch.zeros(iters, dtype=torch.float32, device=device)
+        inv_numel = 1.0 / float(gbs * seq * hidden)               # MSELoss('mean') over the GLOBAL batch
+        x_buf = torch.empty((lbs,) + tuple(x_all.shape[1:]), dtype=x_all.dtype, device=device)
+        ref_buf = torch.empty_like(x_buf)
+
+        for it in range(iters):
+            idx = idx_dev[it]
+            ops.gather_rows(x_all, idx, out=x_buf)
+            ops.gather_rows(ref_all, idx, out=ref_buf)
+            kw = dict(static_kw)
+            if per_sample_kw:
+                li = idx.long()
+                for key, val in per_sample_kw.items():
+                    kw[key] = val.index_select(0, li)
+            mask_rows = None
+            num_elm = 1
+            if token_masks is not None:
+                mask_rows = token_masks.index_select(0, idx.long()).reshape(-1).contiguous()
+                num_elm = max(1, sum(valid_per_sample[i] for i in batches[it]))
+            for wl in wrapped.values():
+                wl.grad_accumulate = False
+            pred = self.block_forward(block, x_buf, kw)
+            pred2d = pred.reshape(-1, hidden)
+            if pred2d.dtype != torch.bfloat16:
+                pred2d = pred2d.to(torch.bfloat16)
+            dpred = ops.mse_fwd_bwd(pred2d.contiguous(), ref_buf.reshape(-1, hidden), mask_rows, inv_numel, 1000.0,
+                                    loss_sum)
+            pred.backward(dpred.view_as(pred).to(pred.dtype))
+            dp.all_reduce_(arena.grads, loss_sum)                  # pre-sign gradients + loss: one exchange
+            ops.best_update(loss_sum, inv_numel, 1.0 / num_elm, it, state, flag, hist)
+            if self.not_use_best_mse:
+                flag.fill_(1 if it == iters - 1 else 0)
+            ops.signsgd_step(arena.params, arena.grads, arena.best, flag, lr_tab, it, arena.clamp_begin, 1.0)
+
+        st = state.cpu().tolist()                                   # the only host sync of the block
+        res.losses = hist.cpu().tolist()
+        res.best_loss, res.best_iter = st[0], int(st[2])
+        res.init_loss = res.losses[0]
+        if self.not_use_best_mse:
+            res.best_iter, res.best_loss = iters - 1, res.losses[-1]
+        with torch.no_grad():
+            self.unwrapper_block(block, wrapped, arena)
+        return {n: arena.best_views(n) for n in wrapped}
+
+
+def _to_device(v, device):
+    if isinstance(v, torch.Tensor):
+        return v.to(device)
+    if isinstance(v, (list, tuple)):
+        return type(v)(_to_device(i, device) for i in v)
+    return v

@@ -1,0 +1,130 @@
+"""Tunable fake-quant linear for the SignRound loop -- host-side mirror of auto_round/wrapper.py.
+
+`WrapperLinear` keeps the reference's parameter names (`value`, `min_scale`, `max_scale`, wrapper.py:184-190)
+but the parameters are *views into one flat fp32 arena per block* (see quantizer.TuneArena) and the math runs in
+hand-written sm_100a kernels behind the C ABI:
+
+    forward   ar_fq_linear_fwd      qdq(W; V, scales) -> tcgen05 GEMM           (wrapper.py:517-565)
+    backward  ar_fq_linear_bwd_dx   dX = dY · Wq
+              ar_fq_linear_bwd_dw   dWq = dYᵀ·X with dV / d(min,max)_scale computed in the GEMM epilogue
+                                    (replaces autograd through wrapper.py:273-290)
+
+There is no autograd graph over the weight and no eager fallback.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .schemes import QuantizationScheme
+
+
+class _FQLinearFn(torch.autograd.Function):
+    """y = x · qdq(W)ᵀ (+bias).  `anchor` is a dummy fp32 scalar that requires grad so that backward runs even
+    when x does not (q/k/v projections read the frozen block input)."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, layer: "WrapperLinear"):
+        k = layer.spec.k
+        x2d = x.reshape(-1, k)
+        if x2d.dtype != torch.bfloat16:
+            x2d = x2d.to(torch.bfloat16)
+        x2d = x2d.contiguous()
+        y = ops.fq_linear_fwd(layer.spec, x2d, layer.weight, layer.value, layer.min_scale, layer.max_scale,
+                              layer.weight_min, layer.weight_max, layer.weight_global_scale, layer.bias_bf16,
+                              layer.wq)
+        ctx.layer = layer
+        ctx.x_dtype = x.dtype
+        ctx.save_for_backward(x2d)
+        return y.view(*x.shape[:-1], layer.spec.n)
+
+    @staticmethod
+    def backward(ctx, dy):
+        layer = ctx.layer
+        (x2d,) = ctx.saved_tensors
+        dy2d = dy.reshape(-1, layer.spec.n)
+        if dy2d.dtype != torch.bfloat16:
+            dy2d = dy2d.to(torch.bfloat16)
+        dy2d = dy2d.contiguous()
+        ops.fq_linear_bwd_dw(layer.spec, dy2d, x2d, layer.weight, layer.value, layer.min_scale, layer.max_scale,
+                             layer.weight_min, layer.weight_max, layer.weight_global_scale, layer.grad_value,
+                             layer.grad_min_scale, layer.grad_max_scale, accumulate=layer.grad_accumulate)
+        layer.grad_accumulate = True           # further micro-batches of this iteration add up
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.fq_linear_bwd_dx(layer.spec, dy2d, layer.wq).view(*dy.shape[:-1], layer.spec.k)
+            if dx.dtype != ctx.x_dtype:
+                dx = dx.to(ctx.x_dtype)
+        return dx, torch.zeros((), dtype=torch.float32, device=dy.device), None
+
+
+class WrapperLinear(nn.Module):
+    """Wraps an nn.Linear for tuning.  All tensors are CUDA; V / min_scale / max_scale and their gradients are
+    slices of the block arena handed in by the quantizer."""
+
+    def __init__(self, orig_layer: nn.Linear, scheme: QuantizationScheme, spec: ops.Spec, arena_views: dict,
+                 global_scale=None):
+        super().__init__()
+        self.orig_layer = orig_layer
+        self.scheme = scheme
+        self.spec = spec
+        w = orig_layer.weight.data
+        if not w.is_cuda:
+            raise RuntimeError("WrapperLinear: the block must be on a CUDA device (no CPU tuning path)")
+        if w.dtype != torch.bfloat16:
+            raise RuntimeError(f"WrapperLinear: weights must be bf16 (amp dtype), got {w.dtype}")
+        self.weight = w.contiguous()
+        b = orig_layer.bias
+        self.bias_bf16 = None if b is None else b.data.to(torch.bfloat16).contiguous()
+        # wrapper.py:154-167 weight_min / weight_max (int types); nv: wrapper.py:108-114 global scale
+        self.weight_min = self.weight_max = None
+        if spec.is_int:
+            self.weight_min, self.weight_max = ops.group_minmax(spec, self.weight)
+        self.weight_global_scale = None
+        if scheme.qdq_name == "nv_fp4":
+            self.weight_global_scale = global_scale if global_scale is not None else ops.nv_global_scale(self.weight)
+        self.value = arena_views["value"]
+        self.max_scale = arena_views["max_scale"]
+        self.min_scale = arena_views.get("min_scale")
+        self.grad_value = arena_views["grad_value"]
+        self.grad_max_scale = arena_views["grad_max_scale"]
+        self.grad_min_scale = arena_views.get("grad_min_scale")
+        self.grad_accumulate = False
+        self.wq = torch.empty_like(self.weight)            # fake-quant weight of the current iteration
+        self.anchor = torch.zeros((), dtype=torch.float32, device=w.device, requires_grad=True)
+        self.params = {"value": self.value, "max_scale": self.max_scale}
+        if self.min_scale is not None:
+            self.params["min_scale"] = self.min_scale
+
+    def forward(self, x):
+        return _FQLinearFn.apply(x, self.anchor, self)
+
+    @torch.no_grad()
+    def unwrapper(self, best: dict):
+        """wrapper.py:345-468: qdq with the best params -> orig_layer.weight; attach scale / zp / global scale."""
+        spec = self.spec
+        wq, scale, zp = ops.qdq_fwd(spec, self.weight, best["value"], best.get("min_scale"), best["max_scale"],
+                                    self.weight_min, self.weight_max, self.weight_global_scale, out_wq=self.wq,
+                                    want_scale=True)
+        lin = self.orig_layer
+        lin.weight.data.copy_(wq)
+        n = spec.n
+        lin.scale = scale.reshape(n, -1)
+        if self.scheme.qdq_name == "int_sym":
+            lin.zp = int(2 ** (self.scheme.bits - 1))
+        elif self.scheme.qdq_name == "int_asym":
+            lin.zp = zp.reshape(n, -1)
+        else:
+            lin.zp = None
+        if self.weight_global_scale is not None:
+            lin.weight_global_scale = self.weight_global_scale
+        return lin
+
+
+def set_module(root: nn.Module, name: str, new: nn.Module):
+    parts = name.split(".")
+    parent = root
+    for p in parts[:-1]:
+        parent = getattr(parent, p)
+    setattr(parent, parts[-1], new)

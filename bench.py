@@ -1,0 +1,343 @@
+"""bench.py -- Llama-3-8B W4A16 (sym, g128) block-wise SignRound calibration on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm  (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W    # the reference's CPU path (oracle port)
+
+A STEP is one transformer block of Llama-3-8B taken through the whole hot path exactly as the reference's
+`quantization tuning time` span counts it (compressors/orchestrator.py:631 -> 792): FP reference forward over all
+128 calibration samples, 200 sign-SGD iterations (batch 8 x 2048 tokens), forward of the tuned block (next block's
+inputs), unwrap, INT4 pack.  All 32 blocks have the same shapes, so `value` (seconds for the 32-block model) is
+ms_per_step * 32; with --steps 32 it is measured outright.  Weights are random-init (HF default init, seed 0),
+calibration tokens are synthetic (seed 1): there is no network.
+
+Both numbers come from ONE pass through the public API `AutoRound(model_on_host, ...).quantize()`:
+  e2e    device time of the whole per-block span: H2D of the block's bf16 weights from pinned host memory ->
+         compute -> D2H of the packed int4 tensors (CUDA events, max over ranks)
+  value  the same span minus the H2D / D2H segments (inputs already resident in HBM)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+LLAMA3_8B = dict(hidden_size=4096, intermediate_size=14336, num_attention_heads=32, num_key_value_heads=8,
+                 vocab_size=128256, rope_theta=500000.0, rms_norm_eps=1e-5, max_position_embeddings=8192)
+N_BLOCKS_FULL = 32
+ITERS, NSAMPLES, SEQLEN, BATCH = 200, 128, 2048, 8
+P_BLOCK = 218_103_808
+P_QKV = 25_165_824
+# linear-layer FLOPs of one step (one block): 200 iterations + 2 full-set forwards
+FLOPS_PER_STEP = ITERS * (BATCH * SEQLEN) * (6 * P_BLOCK - 2 * P_QKV) + 2 * 2 * (NSAMPLES * SEQLEN) * P_BLOCK
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "hbm_gbs": d.get("hbm_gbs"),
+                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained)"}
+    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.5)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+class _Tok:
+    pad_token_id = None
+    pad_token = None
+
+    def save_pretrained(self, *a, **k):
+        return None
+
+
+def build_llama(n_layers: int, device, seed: int = 0):
+    """Random-init Llama-3-8B-shaped model with `n_layers` blocks, bf16, in PINNED host memory.  Initialised on the
+    GPU (fast) with HF's default init, then moved to the host: the public API receives a host model."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    cfg = LlamaConfig(num_hidden_layers=n_layers, tie_word_embeddings=False, **LLAMA3_8B)
+    cfg._attn_implementation = "sdpa"
+    torch.manual_seed(seed)
+    with torch.device("meta"):
+        model = LlamaForCausalLM(cfg)
+    model = model.to_empty(device=device).to(torch.bfloat16)
+    g = torch.Generator(device=device).manual_seed(seed)
+    for name, p in model.named_parameters():
+        if p.dim() >= 2:
+            p.data.normal_(0.0, cfg.initializer_range, generator=g)
+        else:
+            p.data.fill_(1.0)
+    # rotary inv_freq is a non-persistent buffer lost by to_empty(): rebuild it
+    rot = model.model.rotary_emb
+    inv, _ = rot.rope_init_fn(cfg, device) if hasattr(rot, "rope_init_fn") else (None, None)
+    if inv is not None:
+        rot.inv_freq = inv
+        rot.original_inv_freq = inv.clone()
+    model = model.cpu()
+    for p in model.parameters():
+        p.data = p.data.pin_memory()
+    return model.eval()
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from auto_round_b200 import AutoRound, ops
+
+    W, K = args.warmup, args.steps
+    model = build_llama(W + K, dev)
+    tokens = torch.randint(0, LLAMA3_8B["vocab_size"], (NSAMPLES, SEQLEN), generator=torch.Generator().manual_seed(1))
+    dataset = [tokens[i:i + BATCH] for i in range(0, NSAMPLES, BATCH)]
+    ar = AutoRound(model, tokenizer=_Tok(), scheme="W4A16", iters=args.iters, nsamples=NSAMPLES, seqlen=SEQLEN,
+                   batch_size=BATCH, dataset=dataset, device_map=local, seed=42)
+    ar._pack_on_the_fly = True
+
+    ev = {"start": None, "end": None, "segs": []}
+    clocks = ClockSampler(local)
+    launches0 = [0]
+
+    def hook(bi, phase):
+        # phases per block: "h2d0" -> "compute0" -> "d2h0" -> "done"
+        if bi < W:
+            return
+        e = torch.cuda.Event(enable_timing=True)
+        if bi == W and phase == "h2d0":
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            launches0[0] = ops.LAUNCHES[0]
+            clocks.start()
+        e.record()
+        ev["segs"].append((bi, phase, e))
+
+    ar.block_hook = hook
+    ar.quantize()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks.stop_flag = True
+    launches = ops.LAUNCHES[0] - launches0[0]
+
+    by = {}
+    for bi, phase, e in ev["segs"]:
+        by.setdefault(bi, {})[phase] = e
+    e2e_ms = by[W]["h2d0"].elapsed_time(by[W + K - 1]["done"])
+    copy_ms = sum(b["h2d0"].elapsed_time(b["compute0"]) + b["d2h0"].elapsed_time(b["done"]) for b in by.values())
+    comp_ms = e2e_ms - copy_ms
+    t = torch.tensor([e2e_ms, comp_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms, comp_ms = t.tolist()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    ms_per_step = comp_ms / K
+    value_s = ms_per_step * N_BLOCKS_FULL / 1e3
+    e2e_s = (e2e_ms / K) * N_BLOCKS_FULL / 1e3
+    flops_step = FLOPS_PER_STEP * (args.iters / ITERS) if args.iters != ITERS else FLOPS_PER_STEP
+    roof = gemm_roofline(dev, pk)
+    h2d = sum(p.numel() * p.element_size() for p in model.model.layers[0].parameters())
+    d2h = int(P_BLOCK * 0.5 + (P_BLOCK // 128) * (2 + 0.5) + 4096 * 4 * 7)
+    line = {
+        "metric": "Llama-3-8B W4A16 calib wall-clock (s) @200 iters", "value": round(value_s, 3), "unit": "s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_per_step, 2), "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Llama-3-8B W4A16 sym g128 iters=%d nsamples=128 seqlen=2048 batch=8 on %dxB200" % (args.iters, world),
+                   "step": "one decoder block through the tuning span (ref fwd, %d sign-SGD iters, q fwd, unwrap, int4 pack)" % args.iters,
+                   "value_is": "ms_per_step x 32 blocks (identical shapes)%s" % ("" if K != 32 else "; measured over all 32"),
+                   "parallelism": "dp%d (calibration samples sharded, 1 all-reduce of pre-sign grads per iteration)" % world,
+                   "l2": "inputs larger than L2 (per-iteration working set 3.4 GB >> 126 MB)",
+                   "step_tflops_per_gpu": round(flops_step / (ms_per_step / 1e3) / 1e12 / world, 1)},
+        "e2e": {"value": round(e2e_s, 3), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": roof,
+        "step_fraction_of_gemm_roofline": round((flops_step / world / (pk["bf16_tflops"] * 1e12)) / (ms_per_step / 1e3), 4),
+        "losses": {"block0_iter0": ar.block_results[W]["init_loss"], "block0_best": ar.block_results[W]["best_loss"],
+                   "block0_best_iter": ar.block_results[W]["best_iter"]},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def gemm_roofline(dev, pk):
+    """Replay the GEMM launch mix of ONE sign-SGD iteration of a Llama-3-8B block (7 forward, 4 grad-input and
+    7 fused grad-weight launches at T = 16384 tokens) back to back and time it with CUDA events on the launch stream."""
+    from auto_round_b200 import ops
+
+    T = BATCH * SEQLEN
+    shapes = [("q", 4096, 4096, False), ("k", 1024, 4096, False), ("v", 1024, 4096, False), ("o", 4096, 4096, True),
+              ("gate", 14336, 4096, True), ("up", 14336, 4096, True), ("down", 4096, 14336, True)]
+    bufs = {}
+    flops = 0
+    nlaunch = 0
+    for name, n, k, dx in shapes:
+        spec = ops.make_spec("int_sym", 4, 128, n, k)
+        w = (torch.randn(n, k, device=dev) * 0.02).bfloat16()
+        bufs[name] = dict(spec=spec, w=w, x=torch.randn(T, k, device=dev).bfloat16(), dy=torch.randn(T, n, device=dev).bfloat16(),
+                          v=torch.zeros(n, k, device=dev), mn=torch.ones(spec.groups, device=dev), mx=torch.ones(spec.groups, device=dev),
+                          mm=ops.group_minmax(spec, w), dv=torch.empty(n, k, device=dev), dmn=torch.empty(spec.groups, device=dev),
+                          dmx=torch.empty(spec.groups, device=dev), y=torch.empty(T, n, device=dev, dtype=torch.bfloat16),
+                          dxo=torch.empty(T, k, device=dev, dtype=torch.bfloat16), dx=dx)
+        flops += 2 * T * n * k * (3 if dx else 2)
+        nlaunch += 3 if dx else 2
+
+    def one_iter():
+        for b in bufs.values():
+            ops.gemm(b["x"], b["w"], out=b["y"])
+            if b["dx"]:
+                ops.gemm(b["dy"], b["w"], False, True, out=b["dxo"])
+            ops.fq_linear_bwd_dw(b["spec"], b["dy"], b["x"], b["w"], b["v"], b["mn"], b["mx"], b["mm"][0], b["mm"][1], None,
+                                 b["dv"], b["dmn"], b["dmx"])
+
+    for _ in range(3):
+        one_iter()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    s.record()
+    for _ in range(reps):
+        one_iter()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / reps
+    achieved = flops / (ms / 1e3) / 1e12
+    return {"bound": "tensor", "kernel": "ar::gemm_kernel (tcgen05, 128x256x64 tiles; fwd / grad-in / fused grad-w)",
+            "achieved": round(achieved, 1), "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops"], 4),
+            "peak_source": pk["source"], "traffic": None, "flops_per_launch": flops // nlaunch,
+            "avg_launch_ms": round(ms / nlaunch, 4), "launches_per_iteration": nlaunch,
+            "how": "18 GEMM launches of one iteration replayed x10 after 3 warm-ups; operands 3.4 GB >> L2"}
+
+
+def cpu_baseline(budget_s: float = 25.0, threads=None):
+    """The reference's algorithm on the host cores (oracle/signround.py: torch-CPU restatement pinned bit-exact to
+    the reference): sign-SGD iterations of ONE full-shape Llama-3-8B block on a bounded sample (1 sample of 2048
+    tokens per iteration instead of 8), extrapolated to the metric's unit."""
+    from transformers import LlamaConfig
+    from transformers.models.llama.modeling_llama import LlamaDecoderLayer, LlamaRotaryEmbedding
+
+    from oracle import signround as S
+
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    cfg = LlamaConfig(num_hidden_layers=1, **LLAMA3_8B)
+    cfg._attn_implementation = "sdpa"
+    torch.manual_seed(0)
+    blk = LlamaDecoderLayer(cfg, 0).to(torch.bfloat16).eval()
+    nsamp, seq = 2, SEQLEN
+    xs = [torch.randn(1, seq, cfg.hidden_size).to(torch.bfloat16) * 0.02 for _ in range(nsamp)]
+    pos = torch.arange(seq).unsqueeze(0)
+    rot = LlamaRotaryEmbedding(cfg)
+    cos, sin = rot(xs[0], pos)
+    others = {"position_embeddings": [(cos.to(torch.bfloat16), sin.to(torch.bfloat16))], "position_ids": [pos],
+              "attention_mask": None}
+    with torch.no_grad():
+        refs = [S.block_forward(blk, x, {"position_embeddings": others["position_embeddings"][0], "position_ids": pos}) for x in xs]
+    sc = S.LayerScheme(4, 128, True, "int")
+    t0 = time.time()
+    iters_done = 0
+    # time whole iterations until the budget is spent (the first includes wrapper construction, like the reference)
+    n_it = 1
+    res = None
+    while True:
+        t1 = time.time()
+        import copy
+        b2 = copy.deepcopy(blk)
+        res = S.tune_block(b2, xs, others, refs, lambda n, m: sc, iters=n_it, batch_size=1, lr=1.0 / ITERS)
+        dt = time.time() - t1
+        iters_done += n_it
+        if time.time() - t0 + dt > budget_s or iters_done >= 3:
+            break
+    per_iter_1sample = dt / n_it
+    per_iter = per_iter_1sample * BATCH            # batch 8 x 2048 tokens; GEMM-bound, linear in tokens
+    total_s = per_iter * ITERS * N_BLOCKS_FULL
+    return {"value": round(total_s, 1), "unit": "s", "cores": cores, "kind": "port",
+            "sample": "oracle/signround.py (CPU restatement, pinned bit-exact to the reference) on ONE full-shape Llama-3-8B "
+                      "block: %.1f s per sign-SGD iteration at 1x2048 tokens, x8 (batch) x200 (iters) x32 (blocks); "
+                      "EXTRAPOLATED, full-set forwards and pack not included" % per_iter_1sample}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(budget_s=max(20.0, 30.0 * max(args.steps, 1)))
+    line = {"impl": "reference", "metric": "Llama-3-8B W4A16 calib wall-clock (s) @200 iters", "value": cb["value"], "unit": "s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(cb["value"] / N_BLOCKS_FULL * 1e3, 1),
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "Llama-3-8B W4A16 sym g128 iters=200 nsamples=128 seqlen=2048 batch=8, reference CPU path "
+                                   "(the reference has no C/C++ on this path; its Python is restated in oracle/ and timed on the host cores)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--iters", type=int, default=ITERS, help="sign-SGD iterations per block (metric: 200)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

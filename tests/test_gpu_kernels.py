@@ -5,8 +5,8 @@ Tolerances (stated per check):
   * integer / byte outputs (packed words, codes, nibbles, e4m3/e8m0 scales): bit-exact;
   * fake-quant forward (Wq bf16, scale, zp) and dV: bit-exact (same fp32 op sequence, no FMA contraction);
   * d(min/max_scale): fp32 group sums vs the reference's fp16-rounded autograd -> |err| <= 2e-3*|ref| + 1e-3*scale;
-  * bf16 tensor-core GEMMs: fp32-accumulated bf16 products vs an fp32 torch reference -> 1e-2 relative to the
-    output RMS (bf16 output rounding is 2^-9).
+  * bf16 tensor-core GEMMs: fp32-accumulated bf16 products vs an fp32 torch reference ->
+    |d - ref| <= 2^-7*|ref| + 2e-3*rms(ref)  (one bf16 output rounding = 2^-9 relative, plus summation order).
 """
 import os
 
@@ -70,9 +70,10 @@ def test_qdq_golden_fwd_bwd(golden_dir):
         # recomputing min/max inside the kernel must give the same answer
         wq2, _, _ = ops.qdq_fwd(spec, w, v, mn, mx, None, None, gs)
         assert torch.equal(wq2.cpu(), rec["wq"]), key
-        gq = rec["gq"].to(DEV).contiguous()
+        # autograd hands the qdq graph a bf16-rounded dL/dWq (Wq is a bf16 tensor): feed the kernel the same values
+        gq = rec["gq"].to(torch.bfloat16).float().to(DEV).contiguous()
         dv, dmin, dmax = ops.qdq_bwd(spec, w, gq, v, mn, mx, wmin, wmax, gs)
-        ref_dv = rec["dv"]
+        ref_dv = rec["dv"].reshape(n, -1)
         ok = ~torch.isnan(ref_dv)
         assert torch.equal(dv.cpu()[ok], ref_dv[ok]), key
         if rec["dmax"] is not None:
@@ -128,12 +129,14 @@ def test_qdq_vs_oracle_random(name, bits, g):
     assert torch.equal(sc_d.cpu().float().reshape(-1), sc.detach().float().reshape(-1))
     if isinstance(zp, torch.Tensor):
         assert torch.equal(zp_d.cpu().reshape(-1), zp.detach().reshape(-1))
-    dv, dmin, dmax = ops.qdq_bwd(spec, wd, gq.to(DEV), v.to(DEV).contiguous(), mn_d, mx.to(DEV), wmin_d, wmax_d, gs)
-    ok = ~torch.isnan(vr.grad)
+    gq_d = gq.to(torch.bfloat16).float().to(DEV)      # grad w.r.t. the bf16 Wq is bf16-rounded in autograd
+    dv, dmin, dmax = ops.qdq_bwd(spec, wd, gq_d, v.to(DEV).contiguous(), mn_d, mx.to(DEV), wmin_d, wmax_d, gs)
+    ref_dv = vr.grad.reshape(n, -1)
+    ok = ~torch.isnan(ref_dv)
     if name in ("int_sym", "int_asym", "nv_fp4"):
-        assert torch.equal(dv.cpu()[ok], vr.grad[ok])
+        assert torch.equal(dv.cpu()[ok], ref_dv[ok])
     else:  # mx: autograd evaluates (1 - y*dP/dt) + o*dP/dt in fp32; we use the closed form o/t -> 1e-5 relative
-        torch.testing.assert_close(dv.cpu()[ok], vr.grad[ok], rtol=2e-5, atol=1e-7)
+        torch.testing.assert_close(dv.cpu()[ok], ref_dv[ok], rtol=2e-5, atol=1e-7)
     assert _close_scalegrad(dmax, mxr.grad)
     if spec.is_int:
         assert _close_scalegrad(dmin, mnr.grad)
@@ -202,6 +205,14 @@ def test_fp4_nibble_known_answers_gpu():
 
 
 # ----------------------------------------------------------------------------------------------- GEMM
+def _gemm_close(d, ref):
+    ref = ref.float()
+    d = d.float().to(ref.device)
+    rms = ref.pow(2).mean().sqrt()
+    bad = (d - ref).abs() > (2.0 ** -7) * ref.abs() + 2e-3 * rms
+    assert not bool(bad.any()), f"{int(bad.sum())} elements off; max abs err {float((d - ref).abs().max())}, rms {float(rms)}"
+
+
 def _gemm_ref(a, b, a_mn, b_mn, bias=None):
     A = a.float().t() if a_mn else a.float()
     B = b.float().t() if b_mn else b.float()
@@ -218,14 +229,8 @@ def test_gemm_all_majors(a_mn, b_mn, m, n, k):
     a = torch.randn((k, m) if a_mn else (m, k), device=DEV).bfloat16()
     b = torch.randn((k, n) if b_mn else (n, k), device=DEV).bfloat16()
     bias = torch.randn(n, device=DEV).bfloat16()
-    d = ops.gemm(a, b, a_mn, b_mn)
-    ref = _gemm_ref(a, b, a_mn, b_mn)
-    rms = ref.pow(2).mean().sqrt()
-    err = (d.float() - ref).abs().max() / rms
-    assert err < 1e-2, f"max err/rms = {float(err)}"
-    d2 = ops.gemm(a, b, a_mn, b_mn, bias=bias)
-    err2 = (d2.float() - _gemm_ref(a, b, a_mn, b_mn, bias)).abs().max() / rms
-    assert err2 < 1e-2
+    _gemm_close(ops.gemm(a, b, a_mn, b_mn), _gemm_ref(a, b, a_mn, b_mn))
+    _gemm_close(ops.gemm(a, b, a_mn, b_mn, bias=bias), _gemm_ref(a, b, a_mn, b_mn, bias))
 
 
 def test_gemm_llama_shapes_linearity():
@@ -237,9 +242,7 @@ def test_gemm_llama_shapes_linearity():
     w = (torch.randn(n, k, device=DEV) * 0.02).bfloat16()
     y = ops.gemm(x, w)
     rows = torch.randint(0, t, (64,), device=DEV)
-    ref = x[rows].float() @ w.float().t()
-    rms = ref.pow(2).mean().sqrt()
-    assert (y[rows].float() - ref).abs().max() / rms < 1e-2
+    _gemm_close(y[rows], x[rows].float() @ w.float().t())
     y2 = ops.gemm((x * 2).contiguous(), w)
     assert torch.equal(y2, (y.float() * 2).bfloat16())      # scaling by 2 is exact in bf16
 
@@ -283,11 +286,9 @@ def test_fq_linear_fwd_bwd_vs_oracle(name, bits, g):
     scratch = torch.empty_like(wd)
     y = ops.fq_linear_fwd(spec, xd, wd, vd, mnd, mxd, wmin_d, wmax_d, gs, None, scratch)
     assert torch.equal(scratch.cpu(), wq.detach())
-    rms = y_ref.detach().pow(2).mean().sqrt()
-    assert (y.float().cpu() - y_ref.detach()).abs().max() / rms < 1e-2
+    _gemm_close(y.cpu(), y_ref.detach())
     dx = ops.fq_linear_bwd_dx(spec, dyd, scratch)
-    rmsx = xr.grad.pow(2).mean().sqrt()
-    assert (dx.float().cpu() - xr.grad).abs().max() / rmsx < 1e-2
+    _gemm_close(dx.cpu(), xr.grad)
     dv = torch.empty(n, k, dtype=torch.float32, device=DEV)
     dmax = torch.empty(spec.groups, dtype=torch.float32, device=DEV)
     dmin = torch.empty(spec.groups, dtype=torch.float32, device=DEV) if spec.is_int else None
