@@ -342,6 +342,7 @@ class AutoRound:
     def quantize(self):
         model = self.model
         prefix, blocks = find_blocks(model)
+        self.block_prefix, self._blocks = prefix, blocks
         t_cache0 = time.time()
         fp_inputs, others, ids_cache = self.cache_block_inputs(blocks[0])
         torch.cuda.synchronize(self.device)
@@ -407,7 +408,7 @@ class AutoRound:
             raise NotImplementedError(f"format {format!r}: only the auto_round checkpoint format is in scope")
         if not self.quantized:
             raise RuntimeError("call quantize() first")
-        prefix, blocks = find_blocks(self.model)
+        prefix, blocks = self.block_prefix, self._blocks
         if not self._packed:
             for block in blocks:
                 for n, m in list(block.named_modules()):

@@ -255,7 +255,9 @@ class SignRoundQuantizer:
                 others["attention_mask"] = None          # -> is_causal fast path inside the HF attention
         for key, val in others.items():
             if key in SHARED_CACHE_KEYS:
-                v = val[0] if isinstance(val, (list, tuple)) and len(val) >= 1 and not isinstance(val[0], (int, float)) else val
+                # the calibrator stores shared kwargs either raw (tensor / (cos, sin) tuple) or as a LIST with one raw
+                # value per calibration batch (calibration/llm.py:507-545): take the first copy
+                v = val[0] if isinstance(val, list) and len(val) >= 1 else val
                 static[key] = _to_device(v, device)
             elif isinstance(val, (list, tuple)) and len(val) and isinstance(val[0], torch.Tensor):
                 per_sample[key] = torch.cat([v.to(device) for v in val], dim=0)

@@ -183,7 +183,7 @@ def run_ours(args):
     e2e_s = (e2e_ms / K) * N_BLOCKS_FULL / 1e3
     flops_step = FLOPS_PER_STEP * (args.iters / ITERS) if args.iters != ITERS else FLOPS_PER_STEP
     roof = gemm_roofline(dev, pk)
-    h2d = sum(p.numel() * p.element_size() for p in model.model.layers[0].parameters())
+    h2d = (P_BLOCK + 2 * LLAMA3_8B["hidden_size"]) * 2              # bf16 linears + the two RMSNorm weights
     d2h = int(P_BLOCK * 0.5 + (P_BLOCK // 128) * (2 + 0.5) + 4096 * 4 * 7)
     line = {
         "metric": "Llama-3-8B W4A16 calib wall-clock (s) @200 iters", "value": round(value_s, 3), "unit": "s",

@@ -65,6 +65,14 @@ def group_minmax(w: torch.Tensor, group_size: int):
     return torch.clamp(g.min(1)[0], max=0), torch.clamp(g.max(1)[0], min=0)
 
 
+def _cast_ste(x, dtype):
+    """value of x.to(dtype) held in x's own dtype, identity gradient.  NOT reference behaviour: used only by the
+    `grad_fp32=True` variants below, which keep the forward values bit-identical but let autograd accumulate the
+    scale gradient in fp32 instead of the scale tensor's fp16 (tests compare the CUDA kernels, which keep fp32,
+    against this exact-arithmetic gradient; the default path stays bit-exact to the reference)."""
+    return (x.to(dtype).to(x.dtype) - x).detach() + x
+
+
 def _sym_scale_clip(scale, thr):
     # auto_round/data_type/int.py:231-232
     return torch.where(scale < 0, torch.clamp(scale, max=-thr), torch.clamp(scale, min=thr))
@@ -74,7 +82,7 @@ def _sym_scale_clip(scale, thr):
 # int_sym -- auto_round/data_type/int.py:165-238 (quant_tensor_sym), "full range" symmetric
 # --------------------------------------------------------------------------------------------
 def int_sym(w, bits=4, group_size=128, v=0, min_scale=1.0, max_scale=1.0, wmin=None, wmax=None,
-            scale_dtype=torch.float16, q_scale_thresh=1e-5, init_scale=None):
+            scale_dtype=torch.float16, q_scale_thresh=1e-5, init_scale=None, grad_fp32=False):
     g, shape, pad = to_groups(w, group_size)
     maxq = int(2 ** (bits - 1))
     if init_scale is not None:  # int.py:201-216 (alg_ext optimized wrapper)
@@ -87,7 +95,11 @@ def int_sym(w, bits=4, group_size=128, v=0, min_scale=1.0, max_scale=1.0, wmin=N
         lo = -(wmin * min_scale)
         hi = wmax * max_scale
         signed_max = (2 * (hi < lo).int() - 1) * torch.max(hi, lo)
-        scale = _sym_scale_clip((signed_max / maxq).to(scale_dtype), q_scale_thresh).unsqueeze(-1)
+        if grad_fp32:
+            thr = float(torch.tensor(q_scale_thresh).to(scale_dtype))
+            scale = _sym_scale_clip(_cast_ste(signed_max / maxq, scale_dtype), thr).unsqueeze(-1)
+        else:
+            scale = _sym_scale_clip((signed_max / maxq).to(scale_dtype), q_scale_thresh).unsqueeze(-1)
     q = torch.clamp(round_ste(g / scale + v), -maxq, maxq - 1)
     return from_groups((scale * q).to(g.dtype), shape, pad), scale, maxq
 
@@ -109,7 +121,7 @@ def rtn_int_sym(w, bits=4, group_size=128, min_scale=1.0, max_scale=1.0, scale_d
 # int_asym -- auto_round/data_type/int.py:241-298 (quant_tensor_asym)
 # --------------------------------------------------------------------------------------------
 def int_asym(w, bits=4, group_size=128, v=0, min_scale=1.0, max_scale=1.0, wmin=None, wmax=None,
-             scale_dtype=torch.float16, q_scale_thresh=1e-5):
+             scale_dtype=torch.float16, q_scale_thresh=1e-5, grad_fp32=False):
     g, shape, pad = to_groups(w, group_size)
     maxq = int(2 ** bits) - 1
     if wmin is None or wmax is None:
@@ -119,7 +131,10 @@ def int_asym(w, bits=4, group_size=128, v=0, min_scale=1.0, max_scale=1.0, wmin=
         lo, hi = wmin * min_scale, wmax * max_scale
     else:
         lo, hi = wmin, wmax
-    scale = torch.clamp(((hi - lo) / maxq).to(scale_dtype), min=q_scale_thresh)
+    if grad_fp32:
+        scale = torch.clamp(_cast_ste((hi - lo) / maxq, scale_dtype), min=float(torch.tensor(q_scale_thresh).to(scale_dtype)))
+    else:
+        scale = torch.clamp(((hi - lo) / maxq).to(scale_dtype), min=q_scale_thresh)
     zp = round_ste(-lo / scale).unsqueeze(-1)
     scale = scale.unsqueeze(-1)
     q = torch.clamp(round_ste(g / scale + v) + zp, 0, maxq)
