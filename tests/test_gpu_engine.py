@@ -188,7 +188,7 @@ def test_autoround_model_level(golden_dir, tag, tmp_path):
     n0 = sum(int((b0["input_ids"][i] != -100).sum()) for i in b0["batches"][0])
     assert first["losses"][0] * n0 == pytest.approx(b0["losses"][0], rel=2e-2)
     for r in ar.block_results:
-        assert r["best_loss"] <= r["init_loss"]
+        assert r["best_loss"] <= r["init_loss"] * (1 + 1e-6)      # history is fp32, the device state is double
     from safetensors import safe_open
     names = {}
     with safe_open(os.path.join(out_dir, "model.safetensors"), "pt") as f:

@@ -88,7 +88,10 @@ def test_qdq_golden_fwd_bwd(golden_dir):
         dv, dmin, dmax = ops.qdq_bwd(spec, w, gq, v, mn, mx, wmin, wmax, gs)
         ref_dv = rec["dv"].reshape(n, -1)
         ok = ~torch.isnan(ref_dv)
-        assert torch.equal(dv.cpu()[ok], ref_dv[ok]), key
+        if name.startswith("mx"):   # closed form o/t vs autograd's (1 - y*dP/dt) + o*dP/dt: 1e-5 relative
+            torch.testing.assert_close(dv.cpu()[ok], ref_dv[ok], rtol=2e-5, atol=1e-7)
+        else:
+            assert torch.equal(dv.cpu()[ok], ref_dv[ok]), key
         if rec["dmax"] is not None:
             assert _close_scalegrad(dmax, rec["dmax"]), key
         if rec["dmin"] is not None:
