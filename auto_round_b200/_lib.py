@@ -37,8 +37,10 @@ SIGNATURES = {
     "ar_fq_linear_bwd_dx": [_QS, _P, _L, _P, _P, _P],
     "ar_fq_linear_bwd_dw": [_QS, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "ar_mse_fwd_bwd": [_P, _P, _P, _L, _L, _F, _F, _P, _P, _P],
-    "ar_best_update": [_P, _D, _D, _I, _P, _P, _P, _P],
-    "ar_signsgd_step": [_P, _P, _P, _P, _P, _I, _L, _L, _F, _P],
+    "ar_best_update": [_P, _D, _D, _I, _P, _P, _P, _P, _P, _P],
+    "ar_signsgd_step": [_P, _P, _P, _P, _P, _I, _P, _L, _L, _F, _P],
+    "ar_sched_load": [_P, _P, _P, _I, _P, _P, _P, _P],
+    "ar_iter_advance": [_P, _P],
     "ar_gather_rows": [_P, _P, _I, _L, _P, _P],
     "ar_pack_int": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "ar_unpack_int": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],

@@ -302,15 +302,30 @@ class AutoRound:
         static_kw, per_sample_kw = quantizer._prepare_others(others, token_masks, dev)
         outs = []
         bs = self.batch_size
+        n = len(inputs)
+        dp = self.dp
+        # data parallel: rank r forwards its contiguous share of the samples, one all-gather rebuilds the full set
+        per = (n + dp.world - 1) // dp.world
+        lo, hi = (dp.rank * per, min(n, (dp.rank + 1) * per)) if dp.world > 1 else (0, n)
         with _swap_linears(block):
-            for i in range(0, len(inputs), bs):
-                x = torch.cat([t.to(dev) for t in inputs[i:i + bs]], dim=0)
+            for i in range(lo, hi, bs):
+                j = min(i + bs, hi)
+                x = torch.cat([t.to(dev) for t in inputs[i:j]], dim=0)
                 kw = dict(static_kw)
                 for k, v in per_sample_kw.items():
-                    kw[k] = v[i:i + bs]
+                    kw[k] = v[i:j]
                 y = quantizer.block_forward(block, x, kw)
-                outs.extend(torch.split(y.to(self.amp_dtype), 1, dim=0))
-        return outs
+                outs.append(y.to(self.amp_dtype))
+        if dp.world == 1:
+            return [t for y in outs for t in torch.split(y, 1, dim=0)]
+        import torch.distributed as dist
+        local = torch.cat(outs, dim=0) if outs else torch.empty((0,) + tuple(inputs[0].shape[1:]), dtype=self.amp_dtype, device=dev)
+        if local.shape[0] < per:                                   # last rank may own fewer samples: pad
+            pad = local.new_zeros((per - local.shape[0],) + tuple(local.shape[1:]))
+            local = torch.cat([local, pad], dim=0)
+        full = torch.empty((per * dp.world,) + tuple(local.shape[1:]), dtype=local.dtype, device=dev)
+        dist.all_gather_into_tensor(full, local.contiguous(), group=dp.group)
+        return list(torch.split(full[:n], 1, dim=0))
 
     @staticmethod
     def _fuse_nv_global_scales(block: nn.Module, names) -> dict:

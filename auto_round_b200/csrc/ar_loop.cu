@@ -56,8 +56,11 @@ __global__ void __launch_bounds__(256) mse_fwd_bwd_kernel(const uint16_t* __rest
 }
 
 // state: [0]=best_loss [1]=last_loss [2]=best_iter [3]=spare
-__global__ void best_update_kernel(double* loss_sum, double inv_numel, double inv_num_elm, int iter, double* state,
-                                   int32_t* flag, float* loss_hist) {
+__global__ void best_update_kernel(double* loss_sum, double inv_numel, double inv_num_elm, int iter,
+                                   const double* inv_num_elm_ptr, const int32_t* it_ptr, double* state, int32_t* flag,
+                                   float* loss_hist) {
+  if (it_ptr) iter = *it_ptr;                               // device-side schedule (CUDA-graph replay)
+  if (inv_num_elm_ptr) inv_num_elm = *inv_num_elm_ptr;
   const float mean = (float)(*loss_sum * inv_numel);       // MSELoss('mean') result is an fp32 scalar
   const double total = (double)mean * inv_num_elm;          // loss.item() / num_elm
   if (iter == 0) state[0] = 3.4028234663852886e38;          // torch.finfo(torch.float).max
@@ -73,8 +76,10 @@ __device__ __forceinline__ float sgn(float g) { return (g > 0.f) ? 1.f : ((g < 0
 
 __global__ void __launch_bounds__(256) signsgd_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                       float* __restrict__ best, const int32_t* __restrict__ flag,
-                                                      const float* __restrict__ lr_table, int iter, int64_t n4,
+                                                      const float* __restrict__ lr_table, int iter,
+                                                      const int32_t* __restrict__ it_ptr, int64_t n4,
                                                       int64_t clamp_begin4, float clamp_hi) {
+  if (it_ptr) iter = *it_ptr;
   const bool snap = (flag != nullptr) && (*flag != 0) && (best != nullptr);
   const float lr_v = lr_table[2 * iter], lr_s = lr_table[2 * iter + 1];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -104,6 +109,20 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const U4* __restrict__
     dst[d + i] = src[s + i];
 }
 
+// schedule row of the current iteration -> static buffers read by the rest of the (graph-captured) iteration
+__global__ void sched_load_kernel(const int32_t* __restrict__ idx_table, const double* __restrict__ inv_num_elm_table,
+                                  const int32_t* __restrict__ it_ptr, int count, int32_t* __restrict__ cur32,
+                                  int64_t* __restrict__ cur64, double* __restrict__ cur_inv) {
+  const int it = *it_ptr;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const int32_t v = idx_table[(int64_t)it * count + i];
+    if (cur32) cur32[i] = v;
+    if (cur64) cur64[i] = (int64_t)v;
+  }
+  if (threadIdx.x == 0 && cur_inv && inv_num_elm_table) *cur_inv = inv_num_elm_table[it];
+}
+__global__ void iter_advance_kernel(int32_t* it_ptr) { *it_ptr += 1; }
+
 }  // namespace ar
 
 using namespace ar;
@@ -124,16 +143,18 @@ extern "C" int ar_mse_fwd_bwd(const void* pred, const void* ref, const uint8_t* 
   return AR_OK;
 }
 
-extern "C" int ar_best_update(double* loss_sum, double inv_numel, double inv_num_elm, int iter, double* state,
-                              int32_t* flag, float* loss_hist, void* stream) {
+extern "C" int ar_best_update(double* loss_sum, double inv_numel, double inv_num_elm, int iter,
+                              const double* inv_num_elm_ptr, const int32_t* it_ptr, double* state, int32_t* flag,
+                              float* loss_hist, void* stream) {
   AR_REQUIRE(loss_sum && state && flag && iter >= 0, AR_E_BADARG, "bad args");
-  best_update_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(loss_sum, inv_numel, inv_num_elm, iter, state, flag, loss_hist);
+  best_update_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(loss_sum, inv_numel, inv_num_elm, iter, inv_num_elm_ptr, it_ptr, state,
+                                                        flag, loss_hist);
   AR_CHECK_LAUNCH();
   return AR_OK;
 }
 
 extern "C" int ar_signsgd_step(float* p, const float* g, float* best, const int32_t* flag, const float* lr_table, int iter,
-                               int64_t numel, int64_t clamp_begin, float clamp_hi, void* stream) {
+                               const int32_t* it_ptr, int64_t numel, int64_t clamp_begin, float clamp_hi, void* stream) {
   AR_REQUIRE(p && g && lr_table && iter >= 0, AR_E_BADARG, "bad args");
   AR_REQUIRE(numel % 4 == 0 && clamp_begin % 4 == 0, AR_E_UNSUPPORTED, "arena segments must be multiples of 4 floats");
   const int64_t n4 = numel / 4;
@@ -141,8 +162,8 @@ extern "C" int ar_signsgd_step(float* p, const float* g, float* best, const int3
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  signsgd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, best, flag, lr_table, iter, n4, clamp_begin / 4,
-                                                                     clamp_hi);
+  signsgd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, best, flag, lr_table, iter, it_ptr, n4,
+                                                                     clamp_begin / 4, clamp_hi);
   AR_CHECK_LAUNCH();
   return AR_OK;
 }
@@ -156,6 +177,22 @@ extern "C" int ar_gather_rows(const void* src, const int32_t* idx, int count, in
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   gather_rows_kernel<<<dim3((unsigned)bx, (unsigned)count), 256, 0, (cudaStream_t)stream>>>((const U4*)src, idx, row_vec, (U4*)dst);
+  AR_CHECK_LAUNCH();
+  return AR_OK;
+}
+
+extern "C" int ar_sched_load(const int32_t* idx_table, const double* inv_num_elm_table, const int32_t* it_ptr, int count,
+                             int32_t* cur_idx32, int64_t* cur_idx64, double* cur_inv_num_elm, void* stream) {
+  AR_REQUIRE(idx_table && it_ptr && count > 0, AR_E_BADARG, "bad args");
+  sched_load_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(idx_table, inv_num_elm_table, it_ptr, count, cur_idx32, cur_idx64,
+                                                        cur_inv_num_elm);
+  AR_CHECK_LAUNCH();
+  return AR_OK;
+}
+
+extern "C" int ar_iter_advance(int32_t* it_ptr, void* stream) {
+  AR_REQUIRE(it_ptr, AR_E_BADARG, "bad args");
+  iter_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(it_ptr);
   AR_CHECK_LAUNCH();
   return AR_OK;
 }

@@ -17,7 +17,7 @@ from ._lib import DT_INT_ASYM, DT_INT_SYM, DT_MX_FP4, DT_NV_FP4, QSpec
 LAUNCHES = [0]
 _KERNELS_PER_CALL = {"ar_group_minmax": 1, "ar_absmax": 1, "ar_nv_global_scale": 1, "ar_qdq_fwd": 1, "ar_qdq_bwd": 1,
                      "ar_gemm_bf16": 1, "ar_fq_linear_fwd": 2, "ar_fq_linear_bwd_dx": 1, "ar_fq_linear_bwd_dw": 1,
-                     "ar_mse_fwd_bwd": 1, "ar_best_update": 1, "ar_signsgd_step": 1, "ar_gather_rows": 1,
+                     "ar_mse_fwd_bwd": 1, "ar_best_update": 1, "ar_sched_load": 1, "ar_iter_advance": 1, "ar_signsgd_step": 1, "ar_gather_rows": 1,
                      "ar_pack_int": 3, "ar_unpack_int": 1, "ar_pack_fp4_nv": 1, "ar_pack_fp4_mx": 1, "ar_unpack_fp4": 1}
 
 
@@ -205,16 +205,28 @@ def mse_fwd_bwd(pred2d, ref2d, row_mask, inv_numel, upstream, loss_sum, dpred=No
     return dpred
 
 
-def best_update(loss_sum, inv_numel, inv_num_elm, it, state, flag, loss_hist):
-    _check(_lib.load().ar_best_update(_p(loss_sum), float(inv_numel), float(inv_num_elm), int(it), _p(state), _p(flag),
-                                          _p(loss_hist), _stream()), "ar_best_update")
+def best_update(loss_sum, inv_numel, inv_num_elm, it, state, flag, loss_hist, inv_num_elm_dev=None, it_dev=None):
+    """`inv_num_elm_dev` (double [1]) / `it_dev` (int32 [1]) override the host values (CUDA-graph replay)."""
+    _check(_lib.load().ar_best_update(_p(loss_sum), float(inv_numel), float(inv_num_elm), int(it), _p(inv_num_elm_dev),
+                                      _p(it_dev), _p(state), _p(flag), _p(loss_hist), _stream()), "ar_best_update")
 
 
-def signsgd_step(p, g, best, flag, lr_table, it, clamp_begin, clamp_hi=1.0):
+def signsgd_step(p, g, best, flag, lr_table, it, clamp_begin, clamp_hi=1.0, it_dev=None):
     _want(p, torch.float32, "p")
     _want(g, torch.float32, "g")
-    _check(_lib.load().ar_signsgd_step(_p(p), _p(g), _p(best), _p(flag), _p(lr_table), int(it), p.numel(),
-                                           int(clamp_begin), float(clamp_hi), _stream()), "ar_signsgd_step")
+    _check(_lib.load().ar_signsgd_step(_p(p), _p(g), _p(best), _p(flag), _p(lr_table), int(it), _p(it_dev), p.numel(),
+                                       int(clamp_begin), float(clamp_hi), _stream()), "ar_signsgd_step")
+
+
+def sched_load(idx_table, inv_num_elm_table, it_dev, count, cur32, cur64, cur_inv):
+    _want(idx_table, torch.int32, "idx_table")
+    _want(it_dev, torch.int32, "it")
+    _check(_lib.load().ar_sched_load(_p(idx_table), _p(inv_num_elm_table), _p(it_dev), int(count), _p(cur32), _p(cur64),
+                                     _p(cur_inv), _stream()), "ar_sched_load")
+
+
+def iter_advance(it_dev):
+    _check(_lib.load().ar_iter_advance(_p(it_dev), _stream()), "ar_iter_advance")
 
 
 def gather_rows(src, idx_i32, out=None):

@@ -126,6 +126,7 @@ class TuneResult:
     init_loss: float = float("nan")
     batches: list = field(default_factory=list)
     quantized_layers: list = field(default_factory=list)
+    used_cuda_graph: bool = False
 
 
 def default_layer_filter(name: str, module: nn.Module) -> bool:
@@ -164,7 +165,7 @@ class SignRoundQuantizer:
                  minmax_lr: Optional[float] = None, batch_size: int = 8, enable_minmax_tuning: bool = True,
                  enable_quanted_input: bool = True, not_use_best_mse: bool = False, amp_dtype=torch.bfloat16,
                  layer_config: Optional[dict] = None, layer_filter=default_layer_filter,
-                 dp: Optional[DataParallel] = None, gradient_accumulate_steps: int = 1):
+                 dp: Optional[DataParallel] = None, gradient_accumulate_steps: int = 1, use_cuda_graph: bool = True):
         self.scheme = scheme
         self.iters = iters
         self.lr_is_auto = lr is None
@@ -178,6 +179,7 @@ class SignRoundQuantizer:
         self.layer_config = layer_config or {}
         self.layer_filter = layer_filter
         self.dp = dp or DataParallel()
+        self.use_cuda_graph = use_cuda_graph
         if gradient_accumulate_steps != 1:
             raise NotImplementedError("gradient_accumulate_steps != 1 (reference default is 1)")
         self.last_result: Optional[TuneResult] = None
@@ -332,20 +334,27 @@ class SignRoundQuantizer:
         x_buf = torch.empty((lbs,) + tuple(x_all.shape[1:]), dtype=x_all.dtype, device=device)
         ref_buf = torch.empty_like(x_buf)
 
-        for it in range(iters):
-            idx = idx_dev[it]
-            ops.gather_rows(x_all, idx, out=x_buf)
-            ops.gather_rows(ref_all, idx, out=ref_buf)
+        # ---- device-side schedule: iteration counter, current batch indices, 1/num_elm of the current batch
+        it_dev = torch.zeros(1, dtype=torch.int32, device=device)
+        cur32 = torch.zeros(lbs, dtype=torch.int32, device=device)
+        cur64 = torch.zeros(lbs, dtype=torch.int64, device=device)
+        cur_inv = torch.ones(1, dtype=torch.float64, device=device)
+        if token_masks is not None:
+            inv_tab = torch.tensor([1.0 / max(1, sum(valid_per_sample[i] for i in b)) for b in batches],
+                                   dtype=torch.float64, device=device)
+        else:
+            inv_tab = torch.ones(iters, dtype=torch.float64, device=device)
+
+        def fwd_bwd():
+            ops.sched_load(idx_dev, inv_tab, it_dev, lbs, cur32, cur64, cur_inv)
+            ops.gather_rows(x_all, cur32, out=x_buf)
+            ops.gather_rows(ref_all, cur32, out=ref_buf)
             kw = dict(static_kw)
-            if per_sample_kw:
-                li = idx.long()
-                for key, val in per_sample_kw.items():
-                    kw[key] = val.index_select(0, li)
+            for key, val in per_sample_kw.items():
+                kw[key] = val.index_select(0, cur64)
             mask_rows = None
-            num_elm = 1
             if token_masks is not None:
-                mask_rows = token_masks.index_select(0, idx.long()).reshape(-1).contiguous()
-                num_elm = max(1, sum(valid_per_sample[i] for i in batches[it]))
+                mask_rows = token_masks.index_select(0, cur64).reshape(-1)
             for wl in wrapped.values():
                 wl.grad_accumulate = False
             pred = self.block_forward(block, x_buf, kw)
@@ -355,11 +364,56 @@ class SignRoundQuantizer:
             dpred = ops.mse_fwd_bwd(pred2d.contiguous(), ref_buf.reshape(-1, hidden), mask_rows, inv_numel, 1000.0,
                                     loss_sum)
             pred.backward(dpred.view_as(pred).to(pred.dtype))
-            dp.all_reduce_(arena.grads, loss_sum)                  # pre-sign gradients + loss: one exchange
-            ops.best_update(loss_sum, inv_numel, 1.0 / num_elm, it, state, flag, hist)
+
+        def update(last: bool):
+            ops.best_update(loss_sum, inv_numel, 1.0, 0, state, flag, hist, inv_num_elm_dev=cur_inv, it_dev=it_dev)
             if self.not_use_best_mse:
-                flag.fill_(1 if it == iters - 1 else 0)
-            ops.signsgd_step(arena.params, arena.grads, arena.best, flag, lr_tab, it, arena.clamp_begin, 1.0)
+                flag.fill_(1 if last else 0)
+            ops.signsgd_step(arena.params, arena.grads, arena.best, flag, lr_tab, 0, arena.clamp_begin, 1.0, it_dev=it_dev)
+            ops.iter_advance(it_dev)
+
+        def eager_iteration(it):
+            fwd_bwd()
+            dp.all_reduce_(arena.grads, loss_sum)                  # pre-sign gradients + loss: one exchange
+            update(it == iters - 1)
+
+        # ---- CUDA graph: the iteration has static shapes and a device-side schedule, so (after two eager
+        # iterations that also serve as warm-up) it is captured once and replayed.  Under data parallelism the
+        # NCCL all-reduce stays outside the graph: [graph: fwd+bwd] -> all-reduce -> update kernels.
+        n_eager = min(iters, 2)
+        use_graph = self.use_cuda_graph and not self.not_use_best_mse and iters > n_eager + 1
+        graph = None
+        if use_graph:
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                for it in range(n_eager):
+                    eager_iteration(it)
+            torch.cuda.current_stream(device).wait_stream(side)
+            for wl in wrapped.values():
+                wl.anchor.grad = None
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    fwd_bwd()
+                    if dp.world == 1:
+                        update(False)
+            except Exception as e:  # noqa: BLE001 -- capture is an optimisation; the eager loop is the same kernels
+                import warnings
+                warnings.warn(f"CUDA graph capture of the SignRound iteration failed ({e!r}); running eagerly")
+                graph = None
+                torch.cuda.synchronize(device)
+        else:
+            n_eager = 0
+        res.used_cuda_graph = graph is not None
+        for it in range(n_eager if use_graph else 0, iters):
+            if graph is None:
+                eager_iteration(it)
+            else:
+                graph.replay()
+                if dp.world > 1:
+                    dp.all_reduce_(arena.grads, loss_sum)
+                    update(it == iters - 1)
 
         st = state.cpu().tolist()                                   # the only host sync of the block
         res.losses = hist.cpu().tolist()

@@ -149,9 +149,11 @@ int ar_mse_fwd_bwd(const void* pred_bf16, const void* ref_bf16, const uint8_t* r
  *   mean = fp32(*loss_sum * inv_numel); total = mean * inv_num_elm  (= loss.item()/num_elm)
  *   state[0]=best_loss state[1]=last_loss state[2]=best_iter;  *flag = (total < best_loss);  loss_hist[iter]=total
  *   *loss_sum is reset to 0 for the next iteration.  iter==0 initialises best_loss to FLT_MAX.
+ *   inv_num_elm_ptr / it_ptr (device, optional) override the by-value arguments: the loop schedule then lives
+ *   entirely on the device and the whole iteration can be replayed as one CUDA graph.
  */
-int ar_best_update(double* loss_sum, double inv_numel, double inv_num_elm, int iter, double* state, int32_t* flag,
-                   float* loss_hist, void* stream);
+int ar_best_update(double* loss_sum, double inv_numel, double inv_num_elm, int iter, const double* inv_num_elm_ptr,
+                   const int32_t* it_ptr, double* state, int32_t* flag, float* loss_hist, void* stream);
 
 /*
  * Sign-SGD step over a flat fp32 arena [ V of all layers | min/max_scale of all layers ]
@@ -163,7 +165,17 @@ int ar_best_update(double* loss_sum, double inv_numel, double inv_num_elm, int i
  * a CUDA graph.  numel and clamp_begin must be multiples of 4.
  */
 int ar_signsgd_step(float* p, const float* g, float* best, const int32_t* flag, const float* lr_table, int iter,
-                    int64_t numel, int64_t clamp_begin, float clamp_hi, void* stream);
+                    const int32_t* it_ptr, int64_t numel, int64_t clamp_begin, float clamp_hi, void* stream);
+
+/*
+ * Device-side loop schedule (replaces the python loop variable so that one iteration = one CUDA graph):
+ *   ar_sched_load: cur_idx32/64[0..count) = idx_table[*it_ptr][0..count); *cur_inv_num_elm = inv_num_elm_table[*it_ptr]
+ *                  (IndexSampler batches drawn up-front, compressors/utils.py:388-438)
+ *   ar_iter_advance: ++*it_ptr
+ */
+int ar_sched_load(const int32_t* idx_table, const double* inv_num_elm_table, const int32_t* it_ptr, int count,
+                  int32_t* cur_idx32, int64_t* cur_idx64, double* cur_inv_num_elm, void* stream);
+int ar_iter_advance(int32_t* it_ptr, void* stream);
 
 /* Gather `count` sample rows of `row_elems` bf16 each: dst[i] = src[idx[i]]  (BlockForwardRunner._select_batch). */
 int ar_gather_rows(const void* src_bf16, const int32_t* idx, int count, int64_t row_elems, void* dst_bf16,
