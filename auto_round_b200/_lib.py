@@ -41,6 +41,11 @@ SIGNATURES = {
     "ar_signsgd_step": [_P, _P, _P, _P, _P, _I, _P, _L, _L, _F, _P],
     "ar_sched_load": [_P, _P, _P, _I, _P, _P, _P, _P],
     "ar_iter_advance": [_P, _P],
+    "ar_rmsnorm_fwd": [_P, _P, _F, _L, _I, _P, _P, _P],
+    "ar_rmsnorm_bwd": [_P, _P, _P, _P, _L, _I, _P, _I, _P],
+    "ar_rope": [_P, _P, _P, _L, _I, _I, _I, _I, _I, _P, _P],
+    "ar_swiglu_fwd": [_P, _P, _L, _P, _P],
+    "ar_swiglu_bwd": [_P, _P, _P, _L, _P, _P, _P],
     "ar_gather_rows": [_P, _P, _I, _L, _P, _P],
     "ar_pack_int": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "ar_unpack_int": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],

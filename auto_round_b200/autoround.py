@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import export, ops
+from .fused import fused_block_ops
 from .quantizer import DataParallel, SignRoundQuantizer
 from .schemes import QuantizationScheme, parse_scheme
 from .wrapper import set_module
@@ -30,7 +31,7 @@ _SCHEME_KW = ("bits", "group_size", "sym", "data_type", "act_bits", "act_group_s
 _SIGNROUND_KW = ("lr", "minmax_lr", "enable_minmax_tuning", "enable_quanted_input", "not_use_best_mse",
                  "enable_norm_bias_tuning", "dynamic_max_gap", "momentum", "enable_alg_ext", "disable_opt_rtn",
                  "enable_lfq", "nblocks", "quant_lm_head", "scale_dtype", "amp", "to_quant_block_names",
-                 "reference_mask_cast")
+                 "reference_mask_cast", "use_cuda_graph", "fuse_block_ops")
 
 
 class _StopForward(Exception):
@@ -136,7 +137,8 @@ class AutoRound:
         self.low_gpu_mem_usage = low_gpu_mem_usage
         self.seed = seed
         self.sign_kw = {k: kwargs[k] for k in ("lr", "minmax_lr", "enable_minmax_tuning", "enable_quanted_input",
-                                               "not_use_best_mse") if k in kwargs and kwargs[k] is not None}
+                                               "not_use_best_mse", "use_cuda_graph", "fuse_block_ops")
+                        if k in kwargs and kwargs[k] is not None}
         # The reference casts EVERY cached non-integer block kwarg to the amp dtype (calibration/inputs.py:96-107,
         # utils/model.py:1972-2000).  Under transformers >= 5 the 4-D attention mask is boolean, so that cast turns it
         # into an additive +1/0 bias (future tokens become visible).  Default: keep the boolean mask (intended causal
@@ -307,7 +309,7 @@ class AutoRound:
         # data parallel: rank r forwards its contiguous share of the samples, one all-gather rebuilds the full set
         per = (n + dp.world - 1) // dp.world
         lo, hi = (dp.rank * per, min(n, (dp.rank + 1) * per)) if dp.world > 1 else (0, n)
-        with _swap_linears(block):
+        with _swap_linears(block), fused_block_ops(block, quantizer.fuse_block_ops):
             for i in range(lo, hi, bs):
                 j = min(i + bs, hi)
                 x = torch.cat([t.to(dev) for t in inputs[i:j]], dim=0)

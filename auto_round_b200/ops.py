@@ -293,3 +293,44 @@ def unpack_fp4(packed, n, k):
     out = torch.empty(n, k, dtype=torch.bfloat16, device=packed.device)
     _check(_lib.load().ar_unpack_fp4(_p(packed), n, k, _p(out), _stream()), "ar_unpack_fp4")
     return out
+
+
+# ------------------------------------------------------------------- fused block glue (csrc/ar_block.cu)
+def rmsnorm_fwd(x2d, w, eps):
+    _want(x2d, torch.bfloat16, "x")
+    _want(w, torch.bfloat16, "w")
+    rows, hidden = x2d.shape
+    y = torch.empty_like(x2d)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    _check(_lib.load().ar_rmsnorm_fwd(_p(x2d), _p(w), float(eps), rows, hidden, _p(y), _p(rstd), _stream()), "ar_rmsnorm_fwd")
+    return y, rstd
+
+
+def rmsnorm_bwd(dy2d, x2d, w, rstd):
+    rows, hidden = x2d.shape
+    dx = torch.empty_like(x2d)
+    _check(_lib.load().ar_rmsnorm_bwd(_p(dy2d), _p(x2d), _p(w), _p(rstd), rows, hidden, _p(dx), 0, _stream()), "ar_rmsnorm_bwd")
+    return dx
+
+
+def rope(x_bshd, cos, sin, backward=False):
+    """x [B,S,H,D] contiguous bf16; cos/sin [1|B, S, D] bf16 contiguous."""
+    _want(x_bshd, torch.bfloat16, "x")
+    _want(cos, torch.bfloat16, "cos")
+    b, s, h, d = x_bshd.shape
+    out = torch.empty_like(x_bshd)
+    _check(_lib.load().ar_rope(_p(x_bshd), _p(cos), _p(sin), b, s, h, d, cos.shape[0], int(backward), _p(out), _stream()), "ar_rope")
+    return out
+
+
+def swiglu_fwd(gate, up):
+    _want(gate, torch.bfloat16, "gate")
+    h = torch.empty_like(gate)
+    _check(_lib.load().ar_swiglu_fwd(_p(gate), _p(up), gate.numel(), _p(h), _stream()), "ar_swiglu_fwd")
+    return h
+
+
+def swiglu_bwd(dh, gate, up):
+    dg, du = torch.empty_like(gate), torch.empty_like(up)
+    _check(_lib.load().ar_swiglu_bwd(_p(dh), _p(gate), _p(up), gate.numel(), _p(dg), _p(du), _stream()), "ar_swiglu_bwd")
+    return dg, du

@@ -27,6 +27,7 @@ import torch.nn as nn
 
 from . import ops
 from .schemes import QuantizationScheme
+from .fused import fused_block_ops
 from .wrapper import WrapperLinear, set_module
 
 SHARED_CACHE_KEYS = ("position_ids", "cache_position", "position_embeddings", "cu_seqlens")  # utils/common.py:676
@@ -165,7 +166,8 @@ class SignRoundQuantizer:
                  minmax_lr: Optional[float] = None, batch_size: int = 8, enable_minmax_tuning: bool = True,
                  enable_quanted_input: bool = True, not_use_best_mse: bool = False, amp_dtype=torch.bfloat16,
                  layer_config: Optional[dict] = None, layer_filter=default_layer_filter,
-                 dp: Optional[DataParallel] = None, gradient_accumulate_steps: int = 1, use_cuda_graph: bool = True):
+                 dp: Optional[DataParallel] = None, gradient_accumulate_steps: int = 1, use_cuda_graph: bool = True,
+                 fuse_block_ops: bool = True):
         self.scheme = scheme
         self.iters = iters
         self.lr_is_auto = lr is None
@@ -180,6 +182,7 @@ class SignRoundQuantizer:
         self.layer_filter = layer_filter
         self.dp = dp or DataParallel()
         self.use_cuda_graph = use_cuda_graph
+        self.fuse_block_ops = fuse_block_ops
         if gradient_accumulate_steps != 1:
             raise NotImplementedError("gradient_accumulate_steps != 1 (reference default is 1)")
         self.last_result: Optional[TuneResult] = None
@@ -377,43 +380,44 @@ class SignRoundQuantizer:
             dp.all_reduce_(arena.grads, loss_sum)                  # pre-sign gradients + loss: one exchange
             update(it == iters - 1)
 
-        # ---- CUDA graph: the iteration has static shapes and a device-side schedule, so (after two eager
-        # iterations that also serve as warm-up) it is captured once and replayed.  Under data parallelism the
-        # NCCL all-reduce stays outside the graph: [graph: fwd+bwd] -> all-reduce -> update kernels.
-        n_eager = min(iters, 2)
-        use_graph = self.use_cuda_graph and not self.not_use_best_mse and iters > n_eager + 1
-        graph = None
-        if use_graph:
-            side = torch.cuda.Stream(device=device)
-            side.wait_stream(torch.cuda.current_stream(device))
-            with torch.cuda.stream(side):
-                for it in range(n_eager):
-                    eager_iteration(it)
-            torch.cuda.current_stream(device).wait_stream(side)
-            for wl in wrapped.values():
-                wl.anchor.grad = None
-            try:
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    fwd_bwd()
-                    if dp.world == 1:
-                        update(False)
-            except Exception as e:  # noqa: BLE001 -- capture is an optimisation; the eager loop is the same kernels
-                import warnings
-                warnings.warn(f"CUDA graph capture of the SignRound iteration failed ({e!r}); running eagerly")
-                graph = None
-                torch.cuda.synchronize(device)
-        else:
-            n_eager = 0
-        res.used_cuda_graph = graph is not None
-        for it in range(n_eager if use_graph else 0, iters):
-            if graph is None:
-                eager_iteration(it)
+        with fused_block_ops(block, self.fuse_block_ops):
+            # ---- CUDA graph: the iteration has static shapes and a device-side schedule, so (after two eager
+            # iterations that also serve as warm-up) it is captured once and replayed.  Under data parallelism the
+            # NCCL all-reduce stays outside the graph: [graph: fwd+bwd] -> all-reduce -> update kernels.
+            n_eager = min(iters, 2)
+            use_graph = self.use_cuda_graph and not self.not_use_best_mse and iters > n_eager + 1
+            graph = None
+            if use_graph:
+                side = torch.cuda.Stream(device=device)
+                side.wait_stream(torch.cuda.current_stream(device))
+                with torch.cuda.stream(side):
+                    for it in range(n_eager):
+                        eager_iteration(it)
+                torch.cuda.current_stream(device).wait_stream(side)
+                for wl in wrapped.values():
+                    wl.anchor.grad = None
+                try:
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        fwd_bwd()
+                        if dp.world == 1:
+                            update(False)
+                except Exception as e:  # noqa: BLE001 -- capture is an optimisation; the eager loop is the same kernels
+                    import warnings
+                    warnings.warn(f"CUDA graph capture of the SignRound iteration failed ({e!r}); running eagerly")
+                    graph = None
+                    torch.cuda.synchronize(device)
             else:
-                graph.replay()
-                if dp.world > 1:
-                    dp.all_reduce_(arena.grads, loss_sum)
-                    update(it == iters - 1)
+                n_eager = 0
+            res.used_cuda_graph = graph is not None
+            for it in range(n_eager if use_graph else 0, iters):
+                if graph is None:
+                    eager_iteration(it)
+                else:
+                    graph.replay()
+                    if dp.world > 1:
+                        dp.all_reduce_(arena.grads, loss_sum)
+                        update(it == iters - 1)
 
         st = state.cpu().tolist()                                   # the only host sync of the block
         res.losses = hist.cpu().tolist()

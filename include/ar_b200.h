@@ -182,6 +182,24 @@ int ar_gather_rows(const void* src_bf16, const int32_t* idx, int count, int64_t 
                    void* stream);
 
 /*
+ * Fused elementwise ops of a Llama-family decoder block (the non-GEMM work between the fake-quant linears of the
+ * block forward/backward that `quantize_block` drives through the HF layer; they replace ATen eager chains, not a
+ * reference kernel).  bf16 in/out, fp32 math, same rounding points as the HF eager code.
+ *   rmsnorm: y = w * bf16(x * rsqrt(mean(x^2) + eps));  rstd [rows] saved for backward; bwd gives dx only (w frozen)
+ *   rope:    x [B,S,H,D] contiguous, cos/sin [table_batch,S,D]; backward != 0 applies the transposed rotation
+ *   swiglu:  h = bf16(silu(gate)) * up ;  bwd: dgate, dup
+ */
+int ar_rmsnorm_fwd(const void* x_bf16, const void* w_bf16, float eps, int64_t rows, int hidden, void* y_bf16, float* rstd,
+                   void* stream);
+int ar_rmsnorm_bwd(const void* dy_bf16, const void* x_bf16, const void* w_bf16, const float* rstd, int64_t rows, int hidden,
+                   void* dx_bf16, int accumulate, void* stream);
+int ar_rope(const void* x_bf16, const void* cos_bf16, const void* sin_bf16, int64_t b, int s, int h, int d, int table_batch,
+            int backward, void* out_bf16, void* stream);
+int ar_swiglu_fwd(const void* gate_bf16, const void* up_bf16, int64_t numel, void* h_bf16, void* stream);
+int ar_swiglu_bwd(const void* dh_bf16, const void* gate_bf16, const void* up_bf16, int64_t numel, void* dgate_bf16,
+                  void* dup_bf16, void* stream);
+
+/*
  * INT pack (GPTQ-compatible int32 words along K, stored transposed) -- replaces
  *   auto_round_extension/torch/qlinear_torch_zp.py:93-150 (zp_minus_one=1, sym: zp_const = 2^(bits-1))
  *   auto_round_extension/torch/qlinear_torch.py:110-168, :170-281 (zp_minus_one=0, zp tensor)
