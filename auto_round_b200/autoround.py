@@ -145,6 +145,7 @@ class AutoRound:
         # semantics, and it enables the is_causal attention path); reference_mask_cast=True reproduces the reference
         # bit-for-bit for parity runs.
         self.reference_mask_cast = bool(kwargs.get("reference_mask_cast", False))
+        self.disable_opt_rtn = bool(kwargs.get("disable_opt_rtn", False))
         self.device = self._resolve_device(device_map)
         self.amp_dtype = torch.bfloat16
         self.dp = self._resolve_dp()
@@ -360,6 +361,8 @@ class AutoRound:
         model = self.model
         prefix, blocks = find_blocks(model)
         self.block_prefix, self._blocks = prefix, blocks
+        if self.iters == 0:
+            return self._quantize_rtn(prefix, blocks)
         t_cache0 = time.time()
         fp_inputs, others, ids_cache = self.cache_block_inputs(blocks[0])
         torch.cuda.synchronize(self.device)
@@ -419,6 +422,41 @@ class AutoRound:
                     layer_cfg[f"{prefix}.{bi}.{n}"] = self.scheme.to_dict()
         self.layer_config_out = layer_cfg
         return model, layer_cfg
+
+    def _quantize_rtn(self, prefix, blocks):
+        """iters == 0 (plain RTN, `disable_opt_rtn=True` in the reference): zero-shot, block by block, no calibration
+        data (orchestrator.py:420 "Zero-shot mode").  The imatrix-weighted scale search of the reference's DEFAULT
+        iters=0 route (opt-RTN) is not built; asking for it fails loudly."""
+        if not self.disable_opt_rtn:
+            raise NotImplementedError("iters=0 defaults to the optimized RTN (scale search with imatrix) in the reference; "
+                                      "only plain RTN is built on B200: pass disable_opt_rtn=True")
+        quantizer = SignRoundQuantizer(self.scheme, iters=0, batch_size=self.batch_size, amp_dtype=self.amp_dtype,
+                                       layer_config=self.layer_config, dp=self.dp)
+        self.quantizer = quantizer
+        t0 = time.time()
+        for bi, block in enumerate(blocks):
+            self._hook(bi, "h2d0")
+            block.to(self.device)
+            for p in block.parameters():
+                p.requires_grad_(False)
+                if p.dtype in (torch.float32, torch.float16):
+                    p.data = p.data.to(self.amp_dtype)
+            self._hook(bi, "compute0")
+            names = [n for n, m in block.named_modules() if quantizer.layer_filter(n, m)]
+            nv_gs = self._fuse_nv_global_scales(block, names) if self.scheme.qdq_name == "nv_fp4" else None
+            done = quantizer.rtn_block(block, None, nv_gs)
+            if self._pack_on_the_fly:
+                for n in done:
+                    export.pack_layer(n, block, quantizer.scheme_for(n, block.get_submodule(n)), self.device,
+                                      out_device=self.device)
+            self._hook(bi, "d2h0")
+            block.to("cpu")
+            self._hook(bi, "done")
+        torch.cuda.synchronize(self.device)
+        self.timings["tuning_s"] = time.time() - t0
+        self.quantized, self._packed = True, self._pack_on_the_fly
+        self.layer_config_out = {}
+        return self.model, self.layer_config_out
 
     def save_quantized(self, output_dir: Optional[str] = None, format: str = "auto_round", inplace: bool = True):
         if format not in ("auto_round", "auto_round:auto_gptq"):

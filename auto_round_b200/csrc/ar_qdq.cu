@@ -66,6 +66,7 @@ __device__ __forceinline__ void make_group(const QArgs& a, int64_t gidx, const f
                                            GroupIn& gi) {
   constexpr int LPG = G / 8;
   gi.thr = a.thr;
+  gi.plain = (a.mn == nullptr) && (a.mx == nullptr);
   ctx.init(a.bits);
   gi.gscale = (IS_FP4 && a.gscale) ? *a.gscale : 0.f;
   gi.mn = (valid && a.mn) ? a.mn[gidx] : 1.f;

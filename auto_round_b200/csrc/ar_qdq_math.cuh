@@ -22,6 +22,8 @@ struct GroupIn {
   float mn, mx;      // min_scale / max_scale of the group (1 when absent)
   float gscale;      // NVFP4 per-tensor global scale
   float thr;         // q_scale_thresh
+  bool plain = false;  // no min/max_scale tensors (RTN, iters == 0): the reference's range math then stays in the
+                       // weight dtype (bf16) because 0-dim / python scales do not promote (int.py:278-286)
 };
 
 struct GroupAcc {
@@ -84,7 +86,7 @@ struct IntAsym {
   __device__ __forceinline__ void setup(const GroupIn& g) {
     lo = g.wmin * g.mn;
     const float hi = g.wmax * g.mx;
-    const float s_raw = f16_round((hi - lo) / kMaxq);
+    const float s_raw = g.plain ? f16_round(bf16_round(bf16_round(hi - lo) / kMaxq)) : f16_round((hi - lo) / kMaxq);
     const float thr = f16_round(g.thr);
     s = fmaxf(s_raw, thr);
     pass = (s_raw >= thr);

@@ -30,7 +30,8 @@ class QuantLinear(nn.Module):
         self.in_features, self.out_features = in_features, out_features
         self.bits, self.group_size, self.sym, self.data_type = scheme.bits, scheme.group_size, scheme.sym, scheme.data_type
         for k, v in buffers.items():
-            self.register_buffer(k, v)
+            # g_idx is rebuilt by the loader (k // group_size); the reference's checkpoints do not carry it
+            self.register_buffer(k, v, persistent=(k != "g_idx"))
         if bias is not None:
             self.register_buffer("bias", bias)
         else:
@@ -44,6 +45,8 @@ def packing_format_of(scheme: QuantizationScheme) -> str:
     """export_to_autoround/export.py:275-280, formats/backends/autoround.py:62-75."""
     if scheme.data_type == "int" and scheme.sym:
         return "auto_round:auto_gptq"
+    if scheme.data_type in ("nv_fp", "mx_fp", "nv_fp4", "mx_fp4"):
+        return "auto_round:llm_compressor"             # what v0.15.0 writes for FP4 (tests/golden/rtn_export_*.pt)
     return "auto_round"
 
 
@@ -99,14 +102,10 @@ def build_quantization_config(scheme: QuantizationScheme, block_names, extra: Op
                               nsamples=128, seqlen=2048, batch_size=8) -> dict:
     """Keys of export_to_autoround/export.py:286-336 after filter_quantization_config (export/utils.py:334-374)."""
     cfg = {"bits": scheme.bits, "group_size": scheme.group_size, "sym": scheme.sym, "data_type": scheme.data_type}
-    if iters != 200:
-        cfg["iters"] = iters
-    if nsamples != 128:
-        cfg["nsamples"] = nsamples
-    if seqlen != 2048:
-        cfg["seqlen"] = seqlen
-    if batch_size != 8:
-        cfg["batch_size"] = batch_size
+    if iters == 0:
+        cfg["enable_quanted_input"] = False            # RTN route of the reference; the default (True) is filtered out
+    cfg["static_attention_granularity"] = "tensor"
+    cfg["static_kv_granularity"] = "tensor"
     cfg["autoround_version"] = AUTOROUND_VERSION
     cfg["block_name_to_quantize"] = block_names
     cfg["quant_method"] = "auto-round"

@@ -242,6 +242,16 @@ class SignRoundQuantizer:
             lin = wl.unwrapper(views)
             set_module(block, name, lin)
 
+    def rtn_block(self, block: nn.Module, wrapped: Optional[dict] = None, nv_global_scales: Optional[dict] = None):
+        """iters == 0 with disable_opt_rtn: round-to-nearest of every eligible linear, no calibration data
+        (algorithms/quantization/base.py:202-255 -> quant_tensor_rtn_sym / the plain dtype function)."""
+        if wrapped is None:
+            wrapped, _ = self.wrapper_block(block, nv_global_scales)
+        with torch.no_grad():
+            for name, wl in wrapped.items():
+                set_module(block, name, wl.unwrapper({}))
+        return list(wrapped)
+
     # ---------------------------------------------------------------------------------------------
     def _stack(self, samples, device):
         if isinstance(samples, torch.Tensor):
@@ -303,9 +313,8 @@ class SignRoundQuantizer:
         res = TuneResult(quantized_layers=list(wrapped))
         self.last_result = res
         if not wrapped or self.iters <= 0:
-            if wrapped:
-                arena.best.copy_(arena.params)
-                self.unwrapper_block(block, wrapped, arena)
+            if wrapped:                                   # iters == 0: plain RTN (data_type/int.py:125-162)
+                self.rtn_block(block, wrapped)
             return {}
 
         static_kw, per_sample_kw = self._prepare_others(

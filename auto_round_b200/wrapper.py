@@ -104,7 +104,8 @@ class WrapperLinear(nn.Module):
     def unwrapper(self, best: dict):
         """wrapper.py:345-468: qdq with the best params -> orig_layer.weight; attach scale / zp / global scale."""
         spec = self.spec
-        wq, scale, zp = ops.qdq_fwd(spec, self.weight, best["value"], best.get("min_scale"), best["max_scale"],
+        # best == {} -> plain RTN (iters == 0): V = 0, scales = 1, range math in the weight dtype like the reference
+        wq, scale, zp = ops.qdq_fwd(spec, self.weight, best.get("value"), best.get("min_scale"), best.get("max_scale"),
                                     self.weight_min, self.weight_max, self.weight_global_scale, out_wq=self.wq,
                                     want_scale=True)
         lin = self.orig_layer

@@ -237,7 +237,7 @@ def main(argv):
 
     import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
-    what = set(argv) or {"qdq", "pack", "block"}
+    what = (set(argv) - {"rtn"}) or ({"qdq", "pack", "block"} if "rtn" not in argv else set())
     if "qdq" in what:
         gen_qdq()
     if "pack" in what:
@@ -251,3 +251,50 @@ def main(argv):
 
 if __name__ == "__main__":
     main(sys.argv[1:])
+
+
+# ---------------------------------------------------------------------------------------------
+# RTN + export fixture: the reference's own `iters=0, disable_opt_rtn=True` path through
+# quantize_and_save(format="auto_round") on the tiny Llama -> every packed tensor of the checkpoint.
+# Deterministic (no tuning), so the B200 path must reproduce the packed integers bit-for-bit.
+# ---------------------------------------------------------------------------------------------
+def gen_rtn_export(tag, scheme_kwargs):
+    import json
+    import tempfile
+
+    from auto_round import AutoRound
+    from safetensors import safe_open
+
+    from oracle.ref_shim import DummyTokenizer
+
+    model = tiny_llama()
+    init_state = {k: v.clone() for k, v in model.state_dict().items()}
+    tokens = torch.randint(0, 128, (8, 16), generator=torch.Generator().manual_seed(1))
+    with tempfile.TemporaryDirectory() as d:
+        ar = AutoRound(model, tokenizer=DummyTokenizer(), iters=0, disable_opt_rtn=True, nsamples=8, seqlen=16, batch_size=4,
+                       dataset=[tokens[:4], tokens[4:]], device_map="cpu", enable_torch_compile=False, seed=42,
+                       **scheme_kwargs)
+        _, folders = ar.quantize_and_save(d, format="auto_round")
+        d = folders[0] if isinstance(folders, (list, tuple)) else folders      # the reference appends e.g. "w4g32/"
+        tensors = {}
+        for fn in sorted(os.listdir(d)):
+            if fn.endswith(".safetensors"):
+                with safe_open(os.path.join(d, fn), "pt") as f:
+                    for k in f.keys():
+                        t = f.get_tensor(k)
+                        tensors[k] = t.view(torch.uint8) if t.dtype == torch.float8_e4m3fn else t
+        qcfg = json.load(open(os.path.join(d, "config.json")))["quantization_config"]
+    keep = {k: v for k, v in tensors.items() if ".layers." in k and "layernorm" not in k}
+    torch.save({"init_state": init_state, "tokens": tokens, "tensors": keep, "quantization_config": qcfg,
+                "scheme_kwargs": scheme_kwargs}, os.path.join(GOLDEN, f"rtn_export_{tag}.pt"))
+    print(f"rtn_export_{tag}.pt: {len(keep)} tensors; config keys {sorted(qcfg)}")
+
+
+if __name__ == "__main__" and "rtn" in sys.argv[1:]:
+    from oracle.ref_shim import import_reference as _imp
+
+    _imp()
+    gen_rtn_export("w4a16_sym_g32", dict(scheme="W4A16", group_size=32))
+    gen_rtn_export("w2a16_asym_g32", dict(scheme="W2A16", group_size=32, sym=False))
+    gen_rtn_export("nvfp4", dict(scheme="NVFP4", act_bits=16, act_data_type="float"))
+    gen_rtn_export("mxfp4", dict(scheme="MXFP4", act_bits=16))
