@@ -359,6 +359,9 @@ class AutoRound:
     # ---------------------------------------------------------------------------------- quantize
     def quantize(self):
         model = self.model
+        if self.iters == 0 and not self.disable_opt_rtn:
+            raise NotImplementedError("iters=0 defaults to the optimized RTN (scale search with imatrix) in the reference; "
+                                      "only plain RTN is built on B200: pass disable_opt_rtn=True")
         prefix, blocks = find_blocks(model)
         self.block_prefix, self._blocks = prefix, blocks
         if self.iters == 0:
