@@ -19,6 +19,8 @@
 // FLOPs per launch = 2*M*N*K; roofline = dense bf16 tensor peak (MEASURED_PEAKS.json: bf16_tflops).
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "ar_qdq_math.cuh"
@@ -133,6 +135,62 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// ---- 2-CTA (cta_group::2) variants: the CTA pair of one TPC shares one UMMA 256 x BN x 16
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the same-offset mbarrier of CTA `cta` of the cluster (mapa + shared::cluster arrive)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 remaddr;\n"
+      "mapa.shared::cluster.u32 remaddr, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [remaddr];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit -> arrive::one on the same-offset mbarrier of BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -177,14 +235,19 @@ struct GemmParams {
   DwParams dw;
 };
 
-template <int BN>
+// CG = 1: one CTA owns a 128 x BN tile.  CG = 2: a CTA pair owns 256 x BN; each CTA stages its own 128 rows of A and
+// HALF of B (BN/2 rows) -- the tensor cores of both SMs read both halves, which halves the smem operand traffic
+// per SM and leaves room for 6 pipeline stages instead of 4.
+template <int BN, int CG>
 struct SmemLayout {
+  static constexpr int kNumStages = (CG == 2) ? 6 : kStages;
+  static constexpr int kBRows = BN / CG;
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;       // 16 KB
-  static constexpr int kBBytes = BN * BLOCK_K * 2;            // 32 KB @ BN=256
+  static constexpr int kBBytes = kBRows * BLOCK_K * 2;        // 32 KB @ BN=256 (16 KB per CTA of a pair)
   static constexpr int kCBytes = BLOCK_M * 64 * 2;            // one 128 x 64 bf16 store box
   static constexpr int kAOff = 0;
-  static constexpr int kBOff = kStages * kABytes;
-  static constexpr int kCOff = kBOff + kStages * kBBytes;
+  static constexpr int kBOff = kNumStages * kABytes;
+  static constexpr int kCOff = kBOff + kNumStages * kBBytes;
   static constexpr int kBarOff = kCOff + 2 * kCBytes;
   static constexpr int kTotal = kBarOff + 256;
 };
@@ -289,22 +352,27 @@ __device__ __forceinline__ void epilogue_dw(const GemmParams& p, uint32_t tmem_a
 }
 
 // ------------------------------------------------------------------------------------------- the kernel
-template <bool A_MN, bool B_MN, int BN, int EPI, class Ctx, int G, bool IS_FP4>
+template <bool A_MN, bool B_MN, int BN, int EPI, class Ctx, int G, bool IS_FP4, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_d, const GemmParams p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, CG>;
+  constexpr int kNS = L::kNumStages;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-  uint64_t* full = bars;                       // [kStages]
-  uint64_t* empty = bars + kStages;            // [kStages]
-  uint64_t* tfull = bars + 2 * kStages;        // [2]
-  uint64_t* tempty = bars + 2 * kStages + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* full = bars;                   // [kNS]   (CG == 2: only the leader CTA's are waited on)
+  uint64_t* empty = bars + kNS;            // [kNS]
+  uint64_t* tfull = bars + 2 * kNS;        // [2]
+  uint64_t* tempty = bars + 2 * kNS + 2;   // [2]     (CG == 2: only the leader's)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNS + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;     // rank inside the CTA pair
+  const bool leader = (cta_rank == 0);
+  const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // scheduling unit: CTA or CTA pair
+  const int num_units = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_tiles = p.m_tiles * p.n_tiles;     // m_tiles counts (128*CG)-row tiles
   const int num_kb = (p.k + BLOCK_K - 1) / BLOCK_K;
   constexpr uint32_t kTmemCols = 2 * BN;       // two accumulator stages (256 or 512: powers of two)
 
@@ -312,13 +380,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_b);
     if (EPI == EPI_STORE) prefetch_tmap(&map_d);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiThreads); }
+    for (int i = 0; i < kNS; ++i) { mbar_init(&full[i], CG); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CG * kEpiThreads); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  if (CG == 2) cluster_sync();                 // peer barriers are initialised before anyone arrives remotely
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2sm(tmem_slot, kTmemCols); else tmem_alloc(tmem_slot, kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -326,49 +397,55 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     // ===================================================================== TMA producer
     if (elect_one()) {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = unit; t < num_tiles; t += num_units) {
         int mt, nt;
         tile_coords(t, p.m_tiles, p.n_tiles, mt, nt);
-        const int m0 = mt * BLOCK_M, n0 = nt * BN;
+        const int m0 = mt * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M;        // this CTA's 128 rows of A / D
+        const int n0 = nt * BN + (int)cta_rank * L::kBRows;                  // this CTA's share of the B rows
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+          const uint32_t s = it % kNS, ph = (it / kNS) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
-          mbar_expect_tx(&full[s], L::kABytes + L::kBBytes);
+          if (CG == 1) mbar_expect_tx(&full[s], L::kABytes + L::kBBytes);
+          else if (leader) mbar_expect_tx(&full[s], 2 * (L::kABytes + L::kBBytes));   // both CTAs' bytes land here
+          else mbar_arrive_cluster(&full[s], 0);
           uint8_t* sa = smem + L::kAOff + s * L::kABytes;
           uint8_t* sb = smem + L::kBOff + s * L::kBBytes;
           const int k0 = kb * BLOCK_K;
+          auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
+            if (CG == 2) tma_load_2d_2sm(dst, map, &full[s], c0, c1); else tma_load_2d(dst, map, &full[s], c0, c1);
+          };
           if (!A_MN) {
-            tma_load_2d(sa, &map_a, &full[s], k0, m0);                       // box {64 k, 128 m}
+            load(sa, &map_a, k0, m0);                                        // box {64 k, 128 m}
           } else {
 #pragma unroll
             for (int i = 0; i < BLOCK_M / 64; ++i)                           // box {64 m, 64 k} per 64-wide atom
-              tma_load_2d(sa + i * (64 * BLOCK_K * 2), &map_a, &full[s], m0 + i * 64, k0);
+              load(sa + i * (64 * BLOCK_K * 2), &map_a, m0 + i * 64, k0);
           }
           if (!B_MN) {
-            tma_load_2d(sb, &map_b, &full[s], k0, n0);                       // box {64 k, BN n}
+            load(sb, &map_b, k0, n0);                                        // box {64 k, kBRows n}
           } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(sb + i * (64 * BLOCK_K * 2), &map_b, &full[s], n0 + i * 64, k0);
+            for (int i = 0; i < L::kBRows / 64; ++i)
+              load(sb + i * (64 * BLOCK_K * 2), &map_b, n0 + i * 64, k0);
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BLOCK_M, BN);
+  } else if (warp == 1 && leader) {
+    // ===================================================================== MMA issuer (leader CTA of a pair)
+    constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BLOCK_M * CG, BN);
     // K-major:  SBO = 8 rows * 128 B (next 8-row core-matrix group), LBO unused;  K step (16 elem) = +32 B
     // MN-major: SBO = 8 k-rows * 128 B, LBO = 64 k-rows * 128 B (next 64-wide MN atom); K step (16 rows) = +2048 B
     constexpr uint32_t a_lbo = A_MN ? (BLOCK_K * 128) : 0, b_lbo = B_MN ? (BLOCK_K * 128) : 0;
     constexpr uint32_t a_kstep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2), b_kstep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
     uint32_t it = 0, local_tile = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local_tile) {
+    for (int t = unit; t < num_tiles; t += num_units, ++local_tile) {
       const uint32_t as = local_tile & 1u, aph = (local_tile >> 1) & 1u;
       mbar_wait(&tempty[as], aph ^ 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+        const uint32_t s = it % kNS, ph = (it / kNS) & 1u;
         mbar_wait(&full[s], ph);
         tc_fence_after();
         if (elect_one()) {
@@ -378,24 +455,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-            umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) umma_bf16_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[s]);                          // frees the smem stage when these MMAs retire
-          if (kb == num_kb - 1) umma_commit(&tfull[as]);   // accumulator complete -> epilogue
+          if (CG == 2) {
+            umma_commit_2sm(&empty[s]);                        // frees the stage in BOTH CTAs when these MMAs retire
+            if (kb == num_kb - 1) umma_commit_2sm(&tfull[as]); // accumulator complete -> both epilogues
+          } else {
+            umma_commit(&empty[s]);
+            if (kb == num_kb - 1) umma_commit(&tfull[as]);
+          }
         }
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp >= kEpiFirstWarp) {
     // ===================================================================== epilogue warps
     const int q = warp & 3;                                // TMEM lane quarter this warp may access
     const int row_in_tile = q * 32 + lane;
     const int epi_tid = threadIdx.x - kEpiFirstWarp * 32;
     uint32_t local_tile = 0, store_idx = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local_tile) {
+    for (int t = unit; t < num_tiles; t += num_units, ++local_tile) {
       int mt, nt;
       tile_coords(t, p.m_tiles, p.n_tiles, mt, nt);
-      const int m0 = mt * BLOCK_M, n0 = nt * BN;
+      const int m0 = mt * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M, n0 = nt * BN;
       const uint32_t as = local_tile & 1u, aph = (local_tile >> 1) & 1u;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
@@ -403,7 +486,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       if constexpr (EPI == EPI_DW) {
         epilogue_dw<Ctx, G, IS_FP4, BN>(p, tmem_acc, m0 + row_in_tile, n0);
         tc_fence_before();
-        mbar_arrive(&tempty[as]);
+        if (CG == 2) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
       } else {
 #pragma unroll 1
         for (int c = 0; c < BN / 64; ++c, ++store_idx) {
@@ -417,7 +500,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           tmem_ld_wait();
           if (c == BN / 64 - 1) {                           // accumulator fully read: hand TMEM back to the MMA warp
             tc_fence_before();
-            mbar_arrive(&tempty[as]);
+            if (CG == 2) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
           }
           const int nbase = n0 + c * 64;
           uint32_t pk[32];
@@ -456,10 +539,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync(); else __syncthreads();     // nobody exits while the peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -513,11 +596,11 @@ static int check_device() {
   return AR_OK;
 }
 
-template <bool A_MN, bool B_MN, int BN, int EPI, class Ctx, int G, bool IS_FP4>
-static int launch(const void* a, const void* b, void* d, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
-                  const GemmParams& base, cudaStream_t st) {
-  using L = SmemLayout<BN>;
-  auto kern = gemm_kernel<A_MN, B_MN, BN, EPI, Ctx, G, IS_FP4>;
+template <bool A_MN, bool B_MN, int BN, int EPI, class Ctx, int G, bool IS_FP4, int CG>
+static int launch_cg(const void* a, const void* b, void* d, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
+                     const GemmParams& base, cudaStream_t st) {
+  using L = SmemLayout<BN, CG>;
+  auto kern = gemm_kernel<A_MN, B_MN, BN, EPI, Ctx, G, IS_FP4, CG>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -529,7 +612,7 @@ static int launch(const void* a, const void* b, void* d, int m, int n, int k, in
   if (!A_MN) rc = make_map(&ma, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, 64, BLOCK_M);   // stored [m, k]
   else rc = make_map(&ma, a, (uint64_t)m, (uint64_t)k, (uint64_t)lda, 64, BLOCK_K);          // stored [k, m]
   if (rc) return rc;
-  if (!B_MN) rc = make_map(&mb, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, 64, BN);
+  if (!B_MN) rc = make_map(&mb, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, 64, L::kBRows);
   else rc = make_map(&mb, b, (uint64_t)n, (uint64_t)k, (uint64_t)ldb, 64, BLOCK_K);
   if (rc) return rc;
   if (EPI == EPI_STORE) {
@@ -540,13 +623,47 @@ static int launch(const void* a, const void* b, void* d, int m, int n, int k, in
   }
   GemmParams p = base;
   p.m = m; p.n = n; p.k = k;
-  p.m_tiles = (m + BLOCK_M - 1) / BLOCK_M;
+  p.m_tiles = (m + BLOCK_M * CG - 1) / (BLOCK_M * CG);
   p.n_tiles = (n + BN - 1) / BN;
   const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, kNumThreads, L::kTotal, st>>>(ma, mb, md, p);
+  const int max_units = sm_count() / CG;
+  const int units = tiles < max_units ? tiles : max_units;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(units * CG));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, md, p);
+  AR_REQUIRE(e == cudaSuccess, (int)e, "gemm launch failed: %s", cudaGetErrorString(e));
   AR_CHECK_LAUNCH();
   return AR_OK;
+}
+
+// CTA pairs (cta_group::2) for anything big enough to fill the machine with 256-row tiles; AR_GEMM_CG=1|2 forces
+static int pick_cg(int m, int n) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("AR_GEMM_CG");
+    forced = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
+  }
+  if (forced) return forced;
+  const long tiles2 = (long)((m + 255) / 256) * ((n + 255) / 256);
+  return (m >= 256 && tiles2 >= sm_count() / 2) ? 2 : 1;
+}
+
+template <bool A_MN, bool B_MN, int BN, int EPI, class Ctx, int G, bool IS_FP4>
+static int launch(const void* a, const void* b, void* d, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
+                  const GemmParams& base, cudaStream_t st) {
+  if (pick_cg(m, n) == 2)
+    return launch_cg<A_MN, B_MN, BN, EPI, Ctx, G, IS_FP4, 2>(a, b, d, m, n, k, lda, ldb, ldd, base, st);
+  return launch_cg<A_MN, B_MN, BN, EPI, Ctx, G, IS_FP4, 1>(a, b, d, m, n, k, lda, ldb, ldd, base, st);
 }
 
 struct NoCtx {};
