@@ -22,6 +22,7 @@ import torch.nn as nn
 
 from . import export, ops
 from .fused import fused_block_ops
+from .moe import unfuse_experts
 from .quantizer import DataParallel, SignRoundQuantizer
 from .schemes import QuantizationScheme, parse_scheme
 from .wrapper import set_module
@@ -384,6 +385,7 @@ class AutoRound:
             tb = time.time()
             self._hook(bi, "h2d0")
             block.to(self.device)                                         # H2D of this block's weights
+            unfuse_experts(block)                                         # MoE: fused 3-D experts -> per-expert nn.Linear
             for p in block.parameters():
                 p.requires_grad_(False)
                 if p.dtype in (torch.float32, torch.float16):
@@ -440,6 +442,7 @@ class AutoRound:
         for bi, block in enumerate(blocks):
             self._hook(bi, "h2d0")
             block.to(self.device)
+            unfuse_experts(block)
             for p in block.parameters():
                 p.requires_grad_(False)
                 if p.dtype in (torch.float32, torch.float16):

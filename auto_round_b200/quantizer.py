@@ -357,6 +357,9 @@ class SignRoundQuantizer:
         else:
             inv_tab = torch.ones(iters, dtype=torch.float64, device=device)
 
+        from .moe import LinearLoopExperts
+        has_moe = any(isinstance(m, LinearLoopExperts) for m in block.modules())   # ragged, data-dependent shapes
+
         def fwd_bwd():
             ops.sched_load(idx_dev, inv_tab, it_dev, lbs, cur32, cur64, cur_inv)
             ops.gather_rows(x_all, cur32, out=x_buf)
@@ -386,6 +389,13 @@ class SignRoundQuantizer:
 
         def eager_iteration(it):
             fwd_bwd()
+            if has_moe:                                            # an expert that saw no token gets NO gradient
+                for wl in wrapped.values():                        # (sign_sgd.py:274-276 skips grad-is-None params)
+                    if not wl.grad_accumulate:
+                        wl.grad_value.zero_()
+                        wl.grad_max_scale.zero_()
+                        if wl.grad_min_scale is not None:
+                            wl.grad_min_scale.zero_()
             dp.all_reduce_(arena.grads, loss_sum)                  # pre-sign gradients + loss: one exchange
             update(it == iters - 1)
 
@@ -394,7 +404,7 @@ class SignRoundQuantizer:
             # iterations that also serve as warm-up) it is captured once and replayed.  Under data parallelism the
             # NCCL all-reduce stays outside the graph: [graph: fwd+bwd] -> all-reduce -> update kernels.
             n_eager = min(iters, 2)
-            use_graph = self.use_cuda_graph and not self.not_use_best_mse and iters > n_eager + 1
+            use_graph = self.use_cuda_graph and not self.not_use_best_mse and iters > n_eager + 1 and not has_moe
             graph = None
             if use_graph:
                 side = torch.cuda.Stream(device=device)
