@@ -415,6 +415,7 @@ class SignRoundQuantizer:
                 torch.cuda.current_stream(device).wait_stream(side)
                 for wl in wrapped.values():
                     wl.anchor.grad = None
+                launches_before = ops.LAUNCHES[0]
                 try:
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
@@ -429,6 +430,9 @@ class SignRoundQuantizer:
             else:
                 n_eager = 0
             res.used_cuda_graph = graph is not None
+            if graph is not None:       # launches recorded once at capture are issued at every replay
+                per_graph = ops.LAUNCHES[0] - launches_before
+                ops.LAUNCHES[0] += per_graph * (iters - n_eager) - per_graph
             for it in range(n_eager if use_graph else 0, iters):
                 if graph is None:
                     eager_iteration(it)

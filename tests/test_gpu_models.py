@@ -143,7 +143,7 @@ def test_mixtral_experts_unfused_and_packed(tmp_path):
         names = set(f.keys())
     for e in range(4):
         for proj in ("gate_proj", "up_proj", "down_proj"):
-            base = f"model.layers.0.mlp.experts.{e}.{proj}"
+            base = f"model.layers.0.block_sparse_moe.experts.{e}.{proj}"      # HF >= 5 names the MoE block so
             assert base + ".weight_packed" in names and base + ".weight_scale" in names, base
     assert "model.layers.0.self_attn.q_proj.weight_packed" in names
     assert not any(k.endswith("gate_up_proj") for k in names)
