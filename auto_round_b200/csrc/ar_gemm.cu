@@ -220,12 +220,13 @@ struct DwParams {                 // EPI_DW: fake-quant backward inputs/outputs
   const uint16_t* wmin;           // bf16 [G] (int types)
   const uint16_t* wmax;
   const float* gscale;            // nv
-  float* dv;                      // fp32 [N,K]
+  void* dv;                       // [N,K] fp32, or bf16 when dv_bf16 (halves the all-reduce volume under DP)
   float* dmin;                    // [G] or null
   float* dmax;                    // [G] or null
   int bits;
   float thr;
   int accumulate;
+  int dv_bf16;
 };
 
 struct GemmParams {
@@ -338,15 +339,38 @@ __device__ __forceinline__ void epilogue_dw(const GemmParams& p, uint32_t tmem_a
         if (d.dmin) d.dmin[gidx] = d.accumulate ? d.dmin[gidx] + gmn : gmn;
       }
     }
-    float* o = d.dv + off;
+    if (d.dv_bf16) {
+      uint16_t* o = reinterpret_cast<uint16_t*>(d.dv) + off;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 q = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
-      if (d.accumulate) {
-        const float4 old = reinterpret_cast<const float4*>(o)[j];
-        q.x += old.x; q.y += old.y; q.z += old.z; q.w += old.w;
+      for (int j = 0; j < 4; ++j) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = out[8 * j + i];
+        if (d.accumulate) {
+          const U4 old = reinterpret_cast<const U4*>(o)[j];
+          const uint32_t u[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            e[2 * i] += bf16_bits_to_f32((uint16_t)(u[i] & 0xffffu));
+            e[2 * i + 1] += bf16_bits_to_f32((uint16_t)(u[i] >> 16));
+          }
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pk[i] = (uint32_t)f32_to_bf16_bits(e[2 * i]) | ((uint32_t)f32_to_bf16_bits(e[2 * i + 1]) << 16);
+        reinterpret_cast<U4*>(o)[j] = U4{pk[0], pk[1], pk[2], pk[3]};
       }
-      reinterpret_cast<float4*>(o)[j] = q;
+    } else {
+      float* o = reinterpret_cast<float*>(d.dv) + off;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 q = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+        if (d.accumulate) {
+          const float4 old = reinterpret_cast<const float4*>(o)[j];
+          q.x += old.x; q.y += old.y; q.z += old.z; q.w += old.w;
+        }
+        reinterpret_cast<float4*>(o)[j] = q;
+      }
     }
   }
 }
@@ -701,7 +725,7 @@ extern "C" int ar_fq_linear_bwd_dx(const ar_qspec* q, const void* dy, int64_t t,
 
 extern "C" int ar_fq_linear_bwd_dw(const ar_qspec* q, const void* dy, const void* x, int64_t t, const void* w, const float* v,
                                    const float* mn, const float* mx, const void* wmin, const void* wmax, const float* gscale,
-                                   float* dv, float* dmin, float* dmax, int accumulate, void* stream) {
+                                   void* dv, int dv_bf16, float* dmin, float* dmax, int accumulate, void* stream) {
   AR_REQUIRE(q && dy && x && w && dv && t > 0, AR_E_BADARG, "null pointer");
   if (int rc = check_device()) return rc;
   const int N = q->n, K = q->k, g = q->group_size;
@@ -711,7 +735,7 @@ extern "C" int ar_fq_linear_bwd_dw(const ar_qspec* q, const void* dy, const void
   AR_REQUIRE(q->dtype != AR_DT_NV_FP4 || gscale, AR_E_BADARG, "nv_fp4 needs gscale");
   GemmParams p{};
   p.dw = DwParams{(const uint16_t*)w, v, mn, mx, (const uint16_t*)wmin, (const uint16_t*)wmax, gscale, dv, dmin, dmax,
-                  q->bits, q->q_scale_thresh, accumulate};
+                  q->bits, q->q_scale_thresh, accumulate, dv_bf16};
   cudaStream_t st = (cudaStream_t)stream;
   // D[N_out, K_out] = sum_t dY[t,n] X[t,k]:  A = dY stored [T,N] (MN-major), B = X stored [T,K] (MN-major)
 #define AR_DW(CTX, GG, FP4) \

@@ -186,9 +186,12 @@ def fq_linear_bwd_dw(spec: Spec, dy2d, x2d, w, v, min_scale, max_scale, wmin, wm
     _want(dy2d, torch.bfloat16, "dy")
     _want(x2d, torch.bfloat16, "x")
     cs = spec.c()
+    if dv.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("dv must be fp32 or bf16")
     _check(_lib.load().ar_fq_linear_bwd_dw(C.byref(cs), _p(dy2d), _p(x2d), dy2d.shape[0], _p(w), _p(v), _p(min_scale),
-                                               _p(max_scale), _p(wmin), _p(wmax), _p(gscale), _p(dv), _p(dmin), _p(dmax),
-                                               int(accumulate), _stream()), "ar_fq_linear_bwd_dw")
+                                           _p(max_scale), _p(wmin), _p(wmax), _p(gscale), _p(dv),
+                                           int(dv.dtype == torch.bfloat16), _p(dmin), _p(dmax), int(accumulate), _stream()),
+           "ar_fq_linear_bwd_dw")
 
 
 def mse_fwd_bwd(pred2d, ref2d, row_mask, inv_numel, upstream, loss_sum, dpred=None, want_grad=True):
@@ -211,11 +214,19 @@ def best_update(loss_sum, inv_numel, inv_num_elm, it, state, flag, loss_hist, in
                                       _p(it_dev), _p(state), _p(flag), _p(loss_hist), _stream()), "ar_best_update")
 
 
-def signsgd_step(p, g, best, flag, lr_table, it, clamp_begin, clamp_hi=1.0, it_dev=None):
+def signsgd_step(p, g, best, flag, lr_table, it, clamp_begin, clamp_hi=1.0, it_dev=None, g_scales=None):
+    """`g`: gradient of the rounding segment p[:clamp_begin] (fp32 or bf16) -- or, when `g_scales` is None, one fp32
+    tensor covering the whole arena; `g_scales`: fp32 gradient of p[clamp_begin:]."""
     _want(p, torch.float32, "p")
-    _want(g, torch.float32, "g")
-    _check(_lib.load().ar_signsgd_step(_p(p), _p(g), _p(best), _p(flag), _p(lr_table), int(it), _p(it_dev), p.numel(),
-                                       int(clamp_begin), float(clamp_hi), _stream()), "ar_signsgd_step")
+    if g_scales is None:
+        _want(g, torch.float32, "g")
+        g, g_scales = g[:clamp_begin], (g[clamp_begin:] if clamp_begin < p.numel() else None)
+    _want(g_scales, torch.float32, "g_scales")
+    if g.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("rounding gradient must be fp32 or bf16")
+    _check(_lib.load().ar_signsgd_step(_p(p), _p(g), int(g.dtype == torch.bfloat16), _p(g_scales), _p(best), _p(flag),
+                                       _p(lr_table), int(it), _p(it_dev), p.numel(), int(clamp_begin), float(clamp_hi),
+                                       _stream()), "ar_signsgd_step")
 
 
 def sched_load(idx_table, inv_num_elm_table, it_dev, count, cur32, cur64, cur_inv):

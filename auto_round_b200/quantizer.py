@@ -68,7 +68,7 @@ def lr_schedule_table(iters: int, lr: float, minmax_lr: float) -> np.ndarray:
 class TuneArena:
     """Flat fp32 storage for every tunable of one block: [ V_0 | V_1 | ... | scales ... ]."""
 
-    def __init__(self, specs: dict, device):
+    def __init__(self, specs: dict, device, grad_dtype=torch.float32):
         off = 0
         self.views = {}
         for name, spec in specs.items():
@@ -86,14 +86,20 @@ class TuneArena:
         self.numel = off
         self.params = torch.zeros(off, dtype=torch.float32, device=device)
         self.params[self.clamp_begin:] = 1.0          # min/max_scale start at 1, V at 0 (wrapper.py:184-190)
-        self.grads = torch.zeros(off, dtype=torch.float32, device=device)
+        # pre-sign gradients: rounding segment in `grad_dtype` (bf16 halves the data-parallel exchange; only the sign of
+        # the all-reduced sum is used), scale segment always fp32
+        self.grads_v = torch.zeros(self.clamp_begin, dtype=grad_dtype, device=device)
+        self.grads_s = torch.zeros(off - self.clamp_begin, dtype=torch.float32, device=device)
         self.best = torch.zeros(off, dtype=torch.float32, device=device)
 
     def layer_views(self, name: str) -> dict:
         out = {}
         for key, (o, n, shape) in self.views[name].items():
             out[key] = self.params[o:o + n].view(shape)
-            out["grad_" + key] = self.grads[o:o + n].view(shape)
+            if key == "value":
+                out["grad_" + key] = self.grads_v[o:o + n].view(shape)
+            else:
+                out["grad_" + key] = self.grads_s[o - self.clamp_begin:o - self.clamp_begin + n].view(shape)
         return out
 
     def best_views(self, name: str) -> dict:
@@ -167,7 +173,7 @@ class SignRoundQuantizer:
                  enable_quanted_input: bool = True, not_use_best_mse: bool = False, amp_dtype=torch.bfloat16,
                  layer_config: Optional[dict] = None, layer_filter=default_layer_filter,
                  dp: Optional[DataParallel] = None, gradient_accumulate_steps: int = 1, use_cuda_graph: bool = True,
-                 fuse_block_ops: bool = True):
+                 fuse_block_ops: bool = True, grad_dtype=None):
         self.scheme = scheme
         self.iters = iters
         self.lr_is_auto = lr is None
@@ -183,6 +189,7 @@ class SignRoundQuantizer:
         self.dp = dp or DataParallel()
         self.use_cuda_graph = use_cuda_graph
         self.fuse_block_ops = fuse_block_ops
+        self.grad_dtype = grad_dtype        # None: fp32 on one GPU, bf16 under data parallelism
         if gradient_accumulate_steps != 1:
             raise NotImplementedError("gradient_accumulate_steps != 1 (reference default is 1)")
         self.last_result: Optional[TuneResult] = None
@@ -227,7 +234,8 @@ class SignRoundQuantizer:
         if not todo:
             return {}, None
         device = next(iter(todo.values()))[0].weight.device
-        arena = TuneArena({n: t[2] for n, t in todo.items()}, device)
+        grad_dtype = self.grad_dtype if self.grad_dtype is not None else (torch.bfloat16 if self.dp.world > 1 else torch.float32)
+        arena = TuneArena({n: t[2] for n, t in todo.items()}, device, grad_dtype)
         wrapped = {}
         for name, (mod, sc, spec) in todo.items():
             gs = None if nv_global_scales is None else nv_global_scales.get(name)
@@ -384,7 +392,8 @@ class SignRoundQuantizer:
             ops.best_update(loss_sum, inv_numel, 1.0, 0, state, flag, hist, inv_num_elm_dev=cur_inv, it_dev=it_dev)
             if self.not_use_best_mse:
                 flag.fill_(1 if last else 0)
-            ops.signsgd_step(arena.params, arena.grads, arena.best, flag, lr_tab, 0, arena.clamp_begin, 1.0, it_dev=it_dev)
+            ops.signsgd_step(arena.params, arena.grads_v, arena.best, flag, lr_tab, 0, arena.clamp_begin, 1.0, it_dev=it_dev,
+                             g_scales=arena.grads_s)
             ops.iter_advance(it_dev)
 
         def eager_iteration(it):
@@ -396,7 +405,7 @@ class SignRoundQuantizer:
                         wl.grad_max_scale.zero_()
                         if wl.grad_min_scale is not None:
                             wl.grad_min_scale.zero_()
-            dp.all_reduce_(arena.grads, loss_sum)                  # pre-sign gradients + loss: one exchange
+            dp.all_reduce_(arena.grads_v, arena.grads_s, loss_sum)   # pre-sign gradients + loss: one exchange
             update(it == iters - 1)
 
         with fused_block_ops(block, self.fuse_block_ops):
@@ -439,7 +448,7 @@ class SignRoundQuantizer:
                 else:
                     graph.replay()
                     if dp.world > 1:
-                        dp.all_reduce_(arena.grads, loss_sum)
+                        dp.all_reduce_(arena.grads_v, arena.grads_s, loss_sum)
                         update(it == iters - 1)
 
         st = state.cpu().tolist()                                   # the only host sync of the block

@@ -129,10 +129,12 @@ int ar_fq_linear_bwd_dx(const ar_qspec* q, const void* dy_bf16, int64_t t, const
  * TMEM -> registers -> (dv, dmin, dmax) without ever materialising dWq.  Outputs are the PRE-sign
  * gradients (sign is taken after the cross-GPU all-reduce, auto_round/.../sign_sgd.py:389).
  * accumulate != 0 adds into dv/dmin/dmax (micro-batches / gradient_accumulate_steps).
+ * dv_bf16 != 0: dv is bf16 [N,K] instead of fp32 (only the SIGN of the all-reduced sum is used by the update; bf16
+ * halves the per-iteration NVLink exchange of the data-parallel path).
  */
 int ar_fq_linear_bwd_dw(const ar_qspec* q, const void* dy_bf16, const void* x_bf16, int64_t t, const void* w_bf16,
                         const float* v, const float* min_scale, const float* max_scale, const void* wmin_bf16,
-                        const void* wmax_bf16, const float* gscale, float* dv, float* dmin, float* dmax,
+                        const void* wmax_bf16, const float* gscale, void* dv, int dv_bf16, float* dmin, float* dmax,
                         int accumulate, void* stream);
 
 /*
@@ -161,11 +163,13 @@ int ar_best_update(double* loss_sum, double inv_numel, double inv_num_elm, int i
  * wrapper.py:257-259):
  *   if (*flag) best[i] = p[i];           (collect_best_params, compressors/utils.py:205-217: PRE-update values)
  *   p[i] -= lr * sign(g[i]);  for i >= clamp_begin: p[i] = clamp(p[i], 0, clamp_hi)
+ *   g_round covers [0, clamp_begin) (fp32, or bf16 if g_round_bf16); g_scales (fp32) covers [clamp_begin, numel).
  * lr_table[2*iter] (rounding lr) / lr_table[2*iter+1] (minmax lr) are read on the device so the step can live in
  * a CUDA graph.  numel and clamp_begin must be multiples of 4.
  */
-int ar_signsgd_step(float* p, const float* g, float* best, const int32_t* flag, const float* lr_table, int iter,
-                    const int32_t* it_ptr, int64_t numel, int64_t clamp_begin, float clamp_hi, void* stream);
+int ar_signsgd_step(float* p, const void* g_round, int g_round_bf16, const float* g_scales, float* best,
+                    const int32_t* flag, const float* lr_table, int iter, const int32_t* it_ptr, int64_t numel,
+                    int64_t clamp_begin, float clamp_hi, void* stream);
 
 /*
  * Device-side loop schedule (replaces the python loop variable so that one iteration = one CUDA graph):

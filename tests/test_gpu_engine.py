@@ -143,7 +143,7 @@ def test_sign_agreement_iteration0(golden_dir):
     agree_all, n_all = 0.0, 0
     for name in names:
         o, n, shape = arena.views[name]["value"]
-        g = arena.grads[o:o + n].view(shape).cpu()
+        g = arena.grads_v[o:o + n].view(shape).float().cpu()
         ref = wrapped[name].value.grad.reshape(shape)
         big = ref.abs() > 0.05 * ref.abs().max()
         agree_all += float((torch.sign(g)[big] == torch.sign(ref)[big]).sum())
