@@ -393,29 +393,37 @@ class AutoRound:
             self._hook(bi, "compute0")
             names = [n for n, m in block.named_modules() if quantizer.layer_filter(n, m)
                      and (quantizer.scheme_for(n, m) is not None) and quantizer.scheme_for(n, m).bits <= 8]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
             # (3) reference outputs of the FP block on the FP inputs  (composer.py:423-429)
             ref_out = self._forward_all(quantizer, block, fp_inputs, others, token_masks)
+            ev[1].record()
             nv_gs = self._fuse_nv_global_scales(block, names) if self.scheme.qdq_name == "nv_fp4" else None
             eff = q_inputs if (q_inputs is not None and quantizer.enable_quanted_input) else fp_inputs
             quantizer.quantize_block(block, eff, others, ref_out, q_inputs, None, input_ids=ids_cache,
                                      nv_global_scales=nv_gs)
             res = quantizer.last_result
+            ev[2].record()
             # (6) outputs of the quantised block feed the next block (composer.py:476-481)
             if quantizer.enable_quanted_input and bi + 1 < nblk:
                 q_inputs = self._forward_all(quantizer, block, eff, others, token_masks)
             else:
                 q_inputs = None
             fp_inputs = ref_out
+            ev[3].record()
             if self._pack_on_the_fly:                                     # immediate_pack (orchestrator.py:327-337)
                 for n in res.quantized_layers:
                     export.pack_layer(n, block, quantizer.scheme_for(n, block.get_submodule(n)), self.device,
                                       out_device=self.device)
+            ev[4].record()
             self._hook(bi, "d2h0")
             block.to("cpu")                                               # packed tensors (or qdq weights) -> host
             self._hook(bi, "done")
             torch.cuda.synchronize(self.device)
+            phases = {k: ev[i].elapsed_time(ev[i + 1]) for i, k in enumerate(("ref_forward_ms", "tune_ms", "q_forward_ms", "pack_ms"))}
             self.block_results.append({"block": f"{prefix}.{bi}", "init_loss": res.init_loss, "best_loss": res.best_loss,
-                                       "best_iter": res.best_iter, "seconds": time.time() - tb, "losses": res.losses})
+                                       "best_iter": res.best_iter, "seconds": time.time() - tb, "losses": res.losses,
+                                       "phases_ms": phases, "cuda_graph": res.used_cuda_graph})
         self.timings["tuning_s"] = time.time() - t0                      # "quantization tuning time" (orchestrator.py:792)
         self.quantized = True
         self._packed = self._pack_on_the_fly

@@ -200,6 +200,9 @@ def run_ours(args):
         "clocks": clocks.summary(),
         "roofline": roof,
         "step_fraction_of_gemm_roofline": round((flops_step / world / (pk["bf16_tflops"] * 1e12)) / (ms_per_step / 1e3), 4),
+        "phases_ms_per_step": {k: round(sum(r["phases_ms"][k] for r in ar.block_results[W:]) / K, 1)
+                               for k in ar.block_results[W]["phases_ms"]},
+        "cuda_graph": bool(ar.block_results[W].get("cuda_graph")),
         "losses": {"block0_iter0": ar.block_results[W]["init_loss"], "block0_best": ar.block_results[W]["best_loss"],
                    "block0_best_iter": ar.block_results[W]["best_iter"]},
     }
