@@ -50,33 +50,59 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock / throttle reasons during the timed region, through NVML in-process (pynvml).  Spawning `nvidia-smi` twice
+    a second takes driver-wide locks and slowed the measured run by ~10 % on one GPU and several-fold on eight, so the
+    CLI is only the fallback, at a 5 s period."""
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nvml = None
 
     def run(self):
+        if self.nvml is not None:
+            n = self.nvml
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self.stop_flag:
+                try:
+                    sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    try:
+                        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    except Exception:  # noqa: BLE001
+                        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    self.rows.append([str(sm), str(self.max_sm)] + ["Active" if (r & b) else "Not Active" for b in bits.values()])
+                except Exception:  # noqa: BLE001
+                    pass
+                time.sleep(0.5)
+            return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                                     capture_output=True, text=True, timeout=10).stdout.strip()
                 if out:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.5)
+            time.sleep(5.0)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"]}
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 class _Tok:
@@ -150,7 +176,8 @@ def run_ours(args):
             if world > 1:
                 dist.barrier()
             launches0[0] = ops.LAUNCHES[0]
-            clocks.start()
+            if rank == 0:
+                clocks.start()
         e.record()
         ev["segs"].append((bi, phase, e))
 
@@ -173,6 +200,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms, comp_ms = t.tolist()
 
+    dp_probe = collective_probe(dev, world) if world > 1 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -206,11 +234,40 @@ def run_ours(args):
         "losses": {"block0_iter0": ar.block_results[W]["init_loss"], "block0_best": ar.block_results[W]["best_loss"],
                    "block0_best_iter": ar.block_results[W]["best_iter"]},
     }
+    if dp_probe is not None:
+        line["dp_probe"] = dp_probe
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def collective_probe(dev, world):
+    """The two data-path collectives of the DP run timed alone (CUDA events, after the timed region): the per-iteration
+    all-reduce of the bf16 pre-sign rounding gradients (one block: 218 M values) and the per-block all-gather that rebuilds
+    the 128 x 2048 x 4096 bf16 block outputs.  Diagnostic only."""
+    import torch.distributed as dist
+
+    g = torch.zeros(P_BLOCK, dtype=torch.bfloat16, device=dev)
+    per = NSAMPLES // world
+    loc = torch.zeros(per, SEQLEN, LLAMA3_8B["hidden_size"], dtype=torch.bfloat16, device=dev)
+    full = torch.empty(per * world, SEQLEN, LLAMA3_8B["hidden_size"], dtype=torch.bfloat16, device=dev)
+    out = {}
+    for name, fn, n, nbytes in (("allreduce_gradv", lambda: dist.all_reduce(g), 10, g.numel() * 2),
+                                ("allgather_outputs", lambda: dist.all_gather_into_tensor(full, loc), 4, full.numel() * 2)):
+        fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        out[name] = {"ms": round(ms, 3), "bytes": int(nbytes), "GBps_algo": round(nbytes / ms / 1e6, 1)}
+    return out
 
 
 def gemm_roofline(dev, pk):

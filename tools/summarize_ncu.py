@@ -41,8 +41,8 @@ def short(name):
     return re.sub(r"\(.*", "", name)
 
 
-def launches(tag):
-    path = os.path.join(GO, "launches_bench.csv")
+def launches(tag, name="launches_bench"):
+    path = os.path.join(GO, f"{name}.csv")
     if not os.path.exists(path):
         return
     rows = read_csv(path)
@@ -58,13 +58,13 @@ def launches(tag):
     for n, t in seq:
         agg[n][0] += 1
         agg[n][1] += t
-    with open(os.path.join(OUT, f"{tag}_launches_bench.csv"), "w") as f:
+    with open(os.path.join(OUT, f"{tag}_{name}.csv"), "w") as f:
         f.write("kernel,launches,total_ms,avg_us,share_pct\n")
         for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"\"{n[:160]}\",{c},{t / 1e6:.3f},{t / c / 1e3:.1f},{100 * t / tot:.2f}\n")
     # one steady-state sign-SGD iteration = launches between two consecutive ar::signsgd_kernel
     pos = [i for i, (n, _) in enumerate(seq) if "signsgd_kernel" in n]
-    lines = [f"# {tag}: ncu launch list of `bench.py --steps 1 --warmup 1 --iters 10 --no-cpu-baseline` (first 6000 launches)",
+    lines = [f"# {tag} ({name}): ncu launch list of `bench.py --steps 1 --warmup 1 --iters 10 --no-cpu-baseline` (first 6000 launches)",
              "", f"total device time {tot / 1e6:.1f} ms over {len(seq)} launches (cold-cache, serialised: compare SHARES)", ""]
     if len(pos) >= 5:
         it = seq[pos[3] + 1: pos[4] + 1]
@@ -81,7 +81,7 @@ def launches(tag):
             a2[n][1] += t
         for n, (c, t) in sorted(a2.items(), key=lambda kv: -kv[1][1])[:28]:
             lines.append(f"| {100 * t / t_it:.2f}% | {t / 1e3:.1f} | {c} | `{n[:110]}` |")
-    with open(os.path.join(OUT, f"{tag}_launches_bench.md"), "w") as f:
+    with open(os.path.join(OUT, f"{tag}_{name}.md"), "w") as f:
         f.write("\n".join(lines) + "\n")
 
 
