@@ -52,6 +52,10 @@ SIGNATURES = {
     "ar_pack_fp4_nv": [_P, _P, _P, _I, _I, _P, _P, _P],
     "ar_pack_fp4_mx": [_P, _P, _I, _I, _P, _P, _P],
     "ar_unpack_fp4": [_P, _I, _I, _P, _P],
+    "ar_search_scale_int": [_P, _P, _L, _P, _I, _QS, _P, _P, _P],
+    "ar_search_scale_nv": [_P, _P, _L, _P, _P, _I, _QS, _P, _P],
+    "ar_search_scale_mx": [_P, _P, _L, _P, _I, _QS, _P, _P],
+    "ar_imatrix_accum": [_P, _L, _I, _P, _P],
 }
 
 _lib = None

@@ -67,9 +67,64 @@ class _GemmLinear(nn.Module):
     def forward(self, x):
         w = self.lin.weight
         x2d = x.reshape(-1, w.shape[1]).to(torch.bfloat16).contiguous()
+        acc = getattr(self.lin, "_ar_imatrix", None)
+        if acc is not None:
+            acc.add(x, x2d)
         b = None if self.lin.bias is None else self.lin.bias.to(torch.bfloat16).contiguous()
         y = ops.gemm(x2d, w.contiguous(), bias=b)
         return y.view(*x.shape[:-1], w.shape[0])
+
+
+class _ImatrixAcc:
+    """Per-layer importance accumulator: sum over tokens of x^2 per input channel + the sample count
+    (collect_imatrix, algorithms/quantization/rtn/quantizer.py:86-105)."""
+
+    def __init__(self, k: int, device):
+        self.sum = torch.zeros(k, dtype=torch.float32, device=device)
+        self.count = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def add(self, x, x2d=None):
+        if x2d is None:
+            x2d = x.reshape(-1, x.shape[-1]).to(torch.bfloat16).contiguous()
+        ops.imatrix_accum(x2d, self.sum)
+        self.count += float(x.shape[0])                      # the reference counts input.shape[0] per call
+
+
+class _collect_imatrix:
+    """Context manager: while active, every listed nn.Linear of the block accumulates its importance matrix during the
+    full-precision forward (register_fp_input_forward_hooks, rtn/quantizer.py:80-105)."""
+
+    def __init__(self, block: nn.Module, names, device):
+        self.lins = {n: block.get_submodule(n) for n in names}
+        self.device = device
+        self.handles = []
+
+    def __enter__(self):
+        for n, lin in self.lins.items():
+            lin._ar_imatrix = _ImatrixAcc(lin.weight.shape[1], self.device)
+            # linears that _swap_linears leaves alone (odd shapes) are reached through a regular forward hook
+            self.handles.append(lin.register_forward_hook(
+                lambda mod, inp, out: mod._ar_imatrix.add(inp[0] if isinstance(inp, (tuple, list)) else inp)))
+        return self
+
+    def __exit__(self, *a):
+        for h in self.handles:
+            h.remove()
+        return False
+
+    def finish(self, dp, normalise: bool) -> dict:
+        """-> {name: importance [K] fp32}; summed over data-parallel ranks; divided by the sample count for the optimized
+        RTN (rtn/quantizer.py:135-138), left as the raw sum for alg_ext (sign_roundv2/quantizer.py:413-428)."""
+        out = {}
+        for n, lin in self.lins.items():
+            acc = lin._ar_imatrix
+            del lin._ar_imatrix
+            dp.all_reduce_(acc.sum, acc.count)
+            if float(acc.count) == 0:
+                out[n] = None                                 # never reached (e.g. an expert no token was routed to)
+                continue
+            out[n] = acc.sum / acc.count if normalise else acc.sum
+        return out
 
 
 class _swap_linears:
@@ -146,6 +201,7 @@ class AutoRound:
         # semantics, and it enables the is_causal attention path); reference_mask_cast=True reproduces the reference
         # bit-for-bit for parity runs.
         self.reference_mask_cast = bool(kwargs.get("reference_mask_cast", False))
+        self._orig_disable_opt_rtn = kwargs.get("disable_opt_rtn")
         self.disable_opt_rtn = bool(kwargs.get("disable_opt_rtn", False))
         self.device = self._resolve_device(device_map)
         self.amp_dtype = torch.bfloat16
@@ -360,13 +416,11 @@ class AutoRound:
     # ---------------------------------------------------------------------------------- quantize
     def quantize(self):
         model = self.model
-        if self.iters == 0 and not self.disable_opt_rtn:
-            raise NotImplementedError("iters=0 defaults to the optimized RTN (scale search with imatrix) in the reference; "
-                                      "only plain RTN is built on B200: pass disable_opt_rtn=True")
         prefix, blocks = find_blocks(model)
         self.block_prefix, self._blocks = prefix, blocks
         if self.iters == 0:
-            return self._quantize_rtn(prefix, blocks)
+            mode = self._rtn_mode()
+            return self._quantize_opt_rtn(prefix, blocks) if mode == "calibrated_opt" else self._quantize_rtn(prefix, blocks, mode)
         t_cache0 = time.time()
         fp_inputs, others, ids_cache = self.cache_block_inputs(blocks[0])
         torch.cuda.synchronize(self.device)
@@ -436,13 +490,27 @@ class AutoRound:
         self.layer_config_out = layer_cfg
         return model, layer_cfg
 
-    def _quantize_rtn(self, prefix, blocks):
-        """iters == 0 (plain RTN, `disable_opt_rtn=True` in the reference): zero-shot, block by block, no calibration
-        data (orchestrator.py:420 "Zero-shot mode").  The imatrix-weighted scale search of the reference's DEFAULT
-        iters=0 route (opt-RTN) is not built; asking for it fails loudly."""
-        if not self.disable_opt_rtn:
-            raise NotImplementedError("iters=0 defaults to the optimized RTN (scale search with imatrix) in the reference; "
-                                      "only plain RTN is built on B200: pass disable_opt_rtn=True")
+    def _rtn_mode(self) -> str:
+        """Which RTN the reference runs for iters == 0 (`_select_rtn_compressor_base_cls`, autoround.py:250-318, and
+        get_quant_func, data_type/utils.py:139-158), pinned by tests/golden/rtn_export_*.pt:
+          plain           `disable_opt_rtn=True`; int asym (no opt_rtn_* function registered); W8 int unless the user
+                          passed disable_opt_rtn=False explicitly (autoround.py:269-276)
+          calibrated_opt  int sym < 8 bit: calibration forward -> imatrix -> weighted scale search.  NVFP4 too: the
+                          reference's routing preview still sees the preset's act_bits=4, asks for activation calibration and
+                          so runs the OptimizedRTN quantizer with its imatrix hooks
+          zero_shot_opt   MXFP4: no calibration, opt_rtn_mx_fp4 with imatrix=None"""
+        name = self.scheme.qdq_name
+        if self.disable_opt_rtn or name == "int_asym":
+            return "plain"
+        if name == "int_sym":
+            if self.scheme.bits >= 8 and self._orig_disable_opt_rtn is None:
+                return "plain"
+            return "calibrated_opt"
+        return "calibrated_opt" if name == "nv_fp4" else "zero_shot_opt"
+
+    def _quantize_rtn(self, prefix, blocks, mode: str = "plain"):
+        """iters == 0, zero-shot (orchestrator.py:420 "Zero-shot mode"): block by block, no calibration data; `mode` is
+        "plain" or "zero_shot_opt" (see _rtn_mode).  The calibrated route is `_quantize_opt_rtn`."""
         quantizer = SignRoundQuantizer(self.scheme, iters=0, batch_size=self.batch_size, amp_dtype=self.amp_dtype,
                                        layer_config=self.layer_config, dp=self.dp)
         self.quantizer = quantizer
@@ -458,7 +526,8 @@ class AutoRound:
             self._hook(bi, "compute0")
             names = [n for n, m in block.named_modules() if quantizer.layer_filter(n, m)]
             nv_gs = self._fuse_nv_global_scales(block, names) if self.scheme.qdq_name == "nv_fp4" else None
-            done = quantizer.rtn_block(block, None, nv_gs)
+            done = quantizer.rtn_block(block, None, nv_gs, imatrices=({} if mode == "zero_shot_opt" else None),
+                                       is_moe=any("experts" in n for n in names))
             if self._pack_on_the_fly:
                 for n in done:
                     export.pack_layer(n, block, quantizer.scheme_for(n, block.get_submodule(n)), self.device,
@@ -466,6 +535,52 @@ class AutoRound:
             self._hook(bi, "d2h0")
             block.to("cpu")
             self._hook(bi, "done")
+        torch.cuda.synchronize(self.device)
+        self.timings["tuning_s"] = time.time() - t0
+        self.quantized, self._packed = True, self._pack_on_the_fly
+        self.layer_config_out = {}
+        return self.model, self.layer_config_out
+
+    def _quantize_opt_rtn(self, prefix, blocks):
+        """iters == 0, `disable_opt_rtn` unset -- the reference's default RTN (OptimizedRTNQuantizer,
+        algorithms/quantization/rtn/quantizer.py:72-140): per block, the full-precision forward over the calibration set
+        collects each linear's importance matrix (sum x^2 per input channel / #samples), then every layer's scale comes
+        from the importance-weighted grid search (ar_search_scale_*).  iters == 0 implies enable_quanted_input=False, so the
+        next block is fed the full-precision outputs (composer.py:423-429, 476-483)."""
+        fp_inputs, others, ids_cache = self.cache_block_inputs(blocks[0])
+        token_masks_cpu = [(ids != -100).reshape(-1) for ids in ids_cache]
+        any_masked = not all(bool(m.all()) for m in token_masks_cpu)
+        token_masks = [m.to(self.device) for m in token_masks_cpu] if any_masked else None
+        quantizer = SignRoundQuantizer(self.scheme, iters=0, batch_size=self.batch_size, amp_dtype=self.amp_dtype,
+                                       layer_config=self.layer_config, dp=self.dp)
+        self.quantizer = quantizer
+        t0 = time.time()
+        for bi, block in enumerate(blocks):
+            self._hook(bi, "h2d0")
+            block.to(self.device)
+            unfuse_experts(block)
+            for p in block.parameters():
+                p.requires_grad_(False)
+                if p.dtype in (torch.float32, torch.float16):
+                    p.data = p.data.to(self.amp_dtype)
+            self._hook(bi, "compute0")
+            names = [n for n, m in block.named_modules() if quantizer.layer_filter(n, m)
+                     and (quantizer.scheme_for(n, m) is not None) and quantizer.scheme_for(n, m).bits <= 8]
+            is_moe = any("experts" in n for n in names)
+            with _collect_imatrix(block, names, self.device) as col:
+                ref_out = self._forward_all(quantizer, block, fp_inputs, others, token_masks)
+            imatrices = col.finish(self.dp, normalise=True)
+            nv_gs = self._fuse_nv_global_scales(block, names) if self.scheme.qdq_name == "nv_fp4" else None
+            done = quantizer.rtn_block(block, None, nv_gs, imatrices=imatrices, is_moe=is_moe)
+            if self._pack_on_the_fly:
+                for n in done:
+                    export.pack_layer(n, block, quantizer.scheme_for(n, block.get_submodule(n)), self.device,
+                                      out_device=self.device)
+            fp_inputs = ref_out
+            self._hook(bi, "d2h0")
+            block.to("cpu")
+            self._hook(bi, "done")
+            self.block_results.append({"block": f"{prefix}.{bi}", "imatrix_layers": len(imatrices)})
         torch.cuda.synchronize(self.device)
         self.timings["tuning_s"] = time.time() - t0
         self.quantized, self._packed = True, self._pack_on_the_fly

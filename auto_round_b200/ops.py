@@ -345,3 +345,92 @@ def swiglu_bwd(dh, gate, up):
     dg, du = torch.empty_like(gate), torch.empty_like(up)
     _check(_lib.load().ar_swiglu_bwd(_p(dh), _p(gate), _p(up), gate.numel(), _p(dg), _p(du), _stream()), "ar_swiglu_bwd")
     return dg, du
+
+
+# ------------------------------------------------------------------------------- optimized RTN / alg_ext searches
+def int_search_table(bits: int, search_ratio: float = 0.75):
+    """Candidate numerators of search_scales (auto_round/data_type/int.py:49-64), base candidate -2^(bits-1) first.
+    Python double arithmetic as in the reference; the kernel multiplies the fp32 cast by the bf16 reciprocal."""
+    nmax = int(2.0 ** (bits - 1))
+    if bits == 2:
+        half, step = 18 * 5, 0.01
+    else:
+        span = nmax * search_ratio
+        step = span / 200 * 2
+        half = int(span / step)
+    return [float(-nmax)] + [-(nmax - step * i) for i in range(-half, half + 1) if i != 0]
+
+
+NV_SEARCH_TABLE = [1.0] + [sv / 100.0 for sv in range(50, 152) if sv / 100.0 != 1.0]   # nvfp.py:359-364
+MX_SEARCH_TABLE = [1.0, 0.5, 2.0]                                                        # mxfp.py:147
+
+
+_TABLES = {}
+
+
+def _table(key, values, device):
+    k = (key, str(device))
+    if k not in _TABLES:
+        _TABLES[k] = torch.tensor(values, dtype=torch.float64).to(torch.float32).to(device)
+    return _TABLES[k]
+
+
+def _qw_args(qw, spec: Spec):
+    if qw is None:
+        return None, 0
+    _want(qw, torch.float32, "qw")
+    if qw.dim() == 1:
+        if qw.numel() != spec.k:
+            raise ValueError(f"importance vector has {qw.numel()} entries, weight has K={spec.k}")
+        return qw, 0
+    if qw.dim() != 2 or qw.shape[0] != spec.n or qw.shape[1] < spec.kpad:
+        raise ValueError("importance matrix must be [N, >=Kpad]")
+    return qw, qw.shape[1]
+
+
+def search_scale_int(spec: Spec, w, qw=None, want_wq=True):
+    """opt_rtn_int_sym (auto_round/data_type/int.py:89-122): returns (scale fp32 [G] holding bf16 values, wq bf16 | None)."""
+    _want(w, torch.bfloat16, "w")
+    qw, stride = _qw_args(qw, spec)
+    coef = _table(("int", spec.bits), int_search_table(spec.bits), w.device)
+    scale = torch.empty(spec.groups, dtype=torch.float32, device=w.device)
+    wq = torch.empty_like(w) if want_wq else None
+    cs = spec.c()
+    _check(_lib.load().ar_search_scale_int(_p(w), _p(qw), stride, _p(coef), coef.numel(), C.byref(cs), _p(scale), _p(wq),
+                                           _stream()), "ar_search_scale_int")
+    return scale, wq
+
+
+def search_scale_nv(spec: Spec, w, qw=None):
+    """search_nvfp4_scale (auto_round/data_type/nvfp.py:331-385): per-group coefficient, fp32 [G]."""
+    _want(w, torch.bfloat16, "w")
+    qw, stride = _qw_args(qw, spec)
+    coef = _table("nv", NV_SEARCH_TABLE, w.device)
+    own_gs = nv_global_scale(w)                       # the search uses the tensor's own global scale
+    out = torch.empty(spec.groups, dtype=torch.float32, device=w.device)
+    cs = spec.c()
+    _check(_lib.load().ar_search_scale_nv(_p(w), _p(qw), stride, _p(own_gs), _p(coef), coef.numel(), C.byref(cs), _p(out),
+                                          _stream()), "ar_search_scale_nv")
+    return out
+
+
+def search_scale_mx(spec: Spec, w, qw=None):
+    """search_mx_scale (auto_round/data_type/mxfp.py:103-169): per-group coefficient in {1, 0.5, 2}, fp32 [G]."""
+    _want(w, torch.bfloat16, "w")
+    qw, stride = _qw_args(qw, spec)
+    coef = _table("mx", MX_SEARCH_TABLE, w.device)
+    out = torch.empty(spec.groups, dtype=torch.float32, device=w.device)
+    cs = spec.c()
+    _check(_lib.load().ar_search_scale_mx(_p(w), _p(qw), stride, _p(coef), coef.numel(), C.byref(cs), _p(out), _stream()),
+           "ar_search_scale_mx")
+    return out
+
+
+def imatrix_accum(x2d, imatrix):
+    """imatrix[k] += sum_rows x^2 (algorithms/quantization/rtn/quantizer.py:86-105), in place."""
+    _want(x2d, torch.bfloat16, "x")
+    _want(imatrix, torch.float32, "imatrix")
+    if x2d.dim() != 2 or imatrix.numel() != x2d.shape[1]:
+        raise ValueError("imatrix_accum: x [rows, K], imatrix [K]")
+    _check(_lib.load().ar_imatrix_accum(_p(x2d), x2d.shape[0], x2d.shape[1], _p(imatrix), _stream()), "ar_imatrix_accum")
+    return imatrix

@@ -250,14 +250,18 @@ class SignRoundQuantizer:
             lin = wl.unwrapper(views)
             set_module(block, name, lin)
 
-    def rtn_block(self, block: nn.Module, wrapped: Optional[dict] = None, nv_global_scales: Optional[dict] = None):
-        """iters == 0 with disable_opt_rtn: round-to-nearest of every eligible linear, no calibration data
-        (algorithms/quantization/base.py:202-255 -> quant_tensor_rtn_sym / the plain dtype function)."""
+    def rtn_block(self, block: nn.Module, wrapped: Optional[dict] = None, nv_global_scales: Optional[dict] = None,
+                  imatrices: Optional[dict] = None, is_moe: bool = False):
+        """iters == 0: round-to-nearest of every eligible linear (algorithms/quantization/base.py:202-255).
+        `imatrices is None` is the zero-shot route (`disable_opt_rtn=True` -> quant_tensor_rtn_sym / the plain dtype
+        function); a dict {layer name: importance [K] or None} selects the optimized RTN (rtn/quantizer.py:108-140), except
+        for routed MoE experts, which the reference sends through plain RTN (base.py:213-226)."""
         if wrapped is None:
             wrapped, _ = self.wrapper_block(block, nv_global_scales)
         with torch.no_grad():
             for name, wl in wrapped.items():
-                set_module(block, name, wl.unwrapper({}))
+                plain = imatrices is None or (is_moe and "expert" in name and "shared_expert" not in name)
+                set_module(block, name, wl.unwrapper({}) if plain else wl.unwrapper_opt_rtn(imatrices.get(name)))
         return list(wrapped)
 
     # ---------------------------------------------------------------------------------------------

@@ -13,6 +13,8 @@ There is no autograd graph over the weight and no eager fallback.
 """
 from __future__ import annotations
 
+from typing import Optional
+
 import torch
 import torch.nn as nn
 
@@ -121,6 +123,70 @@ class WrapperLinear(nn.Module):
         if self.weight_global_scale is not None:
             lin.weight_global_scale = self.weight_global_scale
         return lin
+
+    @torch.no_grad()
+    def unwrapper_opt_rtn(self, imatrix: Optional[torch.Tensor] = None):
+        """iters == 0 without disable_opt_rtn (get_quant_func, data_type/utils.py:139-146): the imatrix-weighted scale
+        search, then the qdq -- opt_rtn_int_sym (int.py:89-122), opt_rtn_nv_fp4 (nvfp.py:388-413), opt_rtn_mx_fp4
+        (mxfp.py:172-230).  int_asym has no opt_rtn_* entry in the reference registry and takes the plain function."""
+        name = self.scheme.qdq_name
+        if name == "int_asym":
+            return self.unwrapper({})
+        spec, lin, n = self.spec, self.orig_layer, self.spec.n
+        w = self.weight
+        if name == "int_sym":
+            qw = importance_weights(imatrix, w, self.scheme.bits, spec.group_size)
+            scale, wq = ops.search_scale_int(spec, w, qw)
+            lin.weight.data.copy_(wq)
+            lin.scale = scale.to(w.dtype).reshape(n, -1)               # the reference keeps the searched scale in bf16
+            lin.zp = int(2 ** (self.scheme.bits - 1))
+            return lin
+        if name == "nv_fp4":
+            qw = importance_weights(imatrix, w, 4, spec.group_size)
+            coeff = ops.search_scale_nv(spec, w, qw)
+        else:
+            qw = importance_weights(imatrix, w.to(torch.float32), 4, spec.group_size)
+            coeff = ops.search_scale_mx(spec, w, qw)
+        wq, scale, _ = ops.qdq_fwd(spec, w, None, None, coeff, None, None, self.weight_global_scale, out_wq=self.wq,
+                                   want_scale=True)
+        lin.weight.data.copy_(wq)
+        lin.scale = scale.reshape(n, -1)
+        lin.zp = None
+        if self.weight_global_scale is not None:
+            lin.weight_global_scale = self.weight_global_scale
+        return lin
+
+
+def importance_weights(imatrix: Optional[torch.Tensor], w: torch.Tensor, bits: int, group_size: int):
+    """Per-element loss weights of the scale searches from the per-channel importance (int.py:107-115).  The common case
+    returns the [K] vector untouched (the kernel broadcasts it over rows and pads K with 1e-5).  Channels whose importance
+    is exactly zero take the reference's repair path (data_type/gguf.py:437-484), materialised here as [N, Kpad]."""
+    if imatrix is None:
+        return None
+    im = imatrix.reshape(-1).to(torch.float32)
+    if bool(torch.min(im) != 0):
+        return im.contiguous()
+    n, k = w.shape
+    kpad = (k + group_size - 1) // group_size * group_size
+    if kpad != k:
+        im = torch.nn.functional.pad(im, (0, kpad - k), value=1e-5)
+        w = torch.nn.functional.pad(w, (0, kpad - k), value=0.0)
+    g = w.reshape(-1, group_size)
+    qw = im.reshape(1, -1).expand(n, -1).reshape(-1, group_size).clone()
+    zero_cnt = torch.sum(qw <= 1e-30, dim=-1)
+    replace = zero_cnt > group_size // 2
+    if bool(replace.any()):
+        if bits <= 3:
+            tmp = torch.abs(g)
+        else:
+            tmp = torch.abs(g) + torch.sqrt(torch.sum(torch.pow(g, 2), dim=-1, keepdim=True) / 32)
+        qw[replace, :] = tmp.to(qw.dtype)[replace, :]
+    mean_replace = (zero_cnt > 0) & (zero_cnt <= group_size // 2)
+    if bool(mean_replace.any()):
+        fill = (torch.sum(qw, dim=-1) / (qw.shape[1] - zero_cnt)).view(-1, 1).expand(-1, qw.shape[1])
+        idx = qw == 0
+        qw[idx] = fill[idx]
+    return qw.reshape(n, kpad).contiguous()
 
 
 def set_module(root: nn.Module, name: str, new: nn.Module):

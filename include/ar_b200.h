@@ -228,6 +228,27 @@ int ar_pack_fp4_mx(const void* wq_bf16, const void* exp_bf16, int n, int k, uint
                    uint8_t* weight_scale_e8m0, void* stream);
 int ar_unpack_fp4(const uint8_t* weight_packed, int n, int k, void* values_bf16, void* stream);
 
+/*
+ * Scale searches of the optimized RTN (iters == 0 default) and of the alg_ext init scale -- replace
+ *   auto_round/data_type/int.py:24-86   search_scales  (+ the clip and bf16 qdq of opt_rtn_int_sym, :89-122)
+ *   auto_round/data_type/nvfp.py:331-385 search_nvfp4_scale      auto_round/data_type/mxfp.py:103-169 search_mx_scale
+ * w bf16 [N,K]; qw = loss weights from the importance matrix: [K] when qw_row_stride == 0 (K padded with 1e-5 as the
+ * reference does), [N, qw_row_stride >= Kpad] when the host materialised the zero-handled matrix (gguf.py:437-484),
+ * NULL = 1.  coef[ncand] is the candidate table, base candidate first: int: -(2^(bits-1) - step*i) (int.py:59-64),
+ * nv: 1.0 then 0.50..1.51, mx: 1.0, 0.5, 2.0.  Outputs are per group, [N * ceil(K/g)] fp32.
+ *   ar_search_scale_int: scale (bf16-valued, threshold-clipped); wq (bf16 [N,K], may be NULL) = the opt-RTN qdq weight
+ *   ar_search_scale_nv / _mx: the winning coefficient (the `init_scale` / `max_scales` of the reference)
+ *   gscale (nv): device scalar 448*6/amax of THIS tensor -- the search ignores the layer's fused global scale
+ */
+int ar_search_scale_int(const void* w_bf16, const float* qw, long long qw_row_stride, const float* coef, int ncand,
+                        const ar_qspec* spec, float* scale, void* wq_bf16, void* stream);
+int ar_search_scale_nv(const void* w_bf16, const float* qw, long long qw_row_stride, const float* gscale,
+                       const float* coef, int ncand, const ar_qspec* spec, float* coeff_out, void* stream);
+int ar_search_scale_mx(const void* w_bf16, const float* qw, long long qw_row_stride, const float* coef, int ncand,
+                       const ar_qspec* spec, float* coeff_out, void* stream);
+/* importance matrix: imatrix[k] += sum over rows of x[row,k]^2 (algorithms/quantization/rtn/quantizer.py:86-105) */
+int ar_imatrix_accum(const void* x_bf16, long long rows, int k, float* imatrix, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

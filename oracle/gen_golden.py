@@ -232,12 +232,60 @@ def gen_block(tag, scheme_kwargs, iters=8, nsamples=8, seqlen=16, batch_size=4):
     print(f"block_{tag}.pt: {len(rec['blocks'])} blocks, losses[0][:3] =", rec["blocks"][0]["losses"][:3])
 
 
+def gen_opt_rtn():
+    """Optimized-RTN functions (iters == 0 default route): search_scales / search_nvfp4_scale / search_mx_scale behind
+    opt_rtn_int_sym, opt_rtn_nv_fp4, opt_rtn_mx_fp4, with and without an importance matrix."""
+    from auto_round.data_type import QUANT_FUNC_WITH_DTYPE as Q
+    from auto_round.data_type.int import search_scales
+    from auto_round.data_type.mxfp import search_mx_scale
+    from auto_round.data_type.nvfp import calculate_gparam, search_nvfp4_scale
+    from auto_round.data_type.utils import reshape_pad_tensor_by_group_size
+
+    out = {}
+    cases = [
+        ("int_sym_w4g128", "opt_rtn_int_sym", dict(bits=4, group_size=128), 16, 256, "im"),
+        ("int_sym_w2g32", "opt_rtn_int_sym", dict(bits=2, group_size=32), 16, 128, "im"),
+        ("int_sym_w3g128", "opt_rtn_int_sym", dict(bits=3, group_size=128), 8, 256, None),
+        ("int_sym_w8g64", "opt_rtn_int_sym", dict(bits=8, group_size=64), 8, 128, "im"),
+        ("int_sym_w4g128_pad", "opt_rtn_int_sym", dict(bits=4, group_size=128), 8, 200, "im"),
+        ("int_sym_w4g32_imzero", "opt_rtn_int_sym", dict(bits=4, group_size=32), 8, 128, "imzero"),
+        ("nv_fp4_g16", "opt_rtn_nv_fp4", dict(bits=4, group_size=16), 16, 128, "im"),
+        ("nv_fp4_g16_noim", "opt_rtn_nv_fp4", dict(bits=4, group_size=16), 8, 64, None),
+        ("mx_fp4_g32", "opt_rtn_mx_fp4", dict(bits=4, group_size=32, data_type="mx_fp4"), 16, 128, "im"),
+    ]
+    for ci, (name, fname, kw, n, k, imk) in enumerate(cases):
+        w = _weights(n, k, 300 + ci)
+        gen = torch.Generator().manual_seed(50 + ci)
+        im = None
+        if imk:
+            im = (torch.rand(k, generator=gen) ** 2 * 40 + 0.01).to(torch.float32)
+            if imk == "imzero":
+                im[:20] = 0          # group 0: > g/2 zeros -> weight-derived importance
+                im[40:44] = 0        # group 1: <= g/2 zeros -> mean fill
+        kwargs = dict(kw)
+        if im is not None:
+            kwargs["imatrix"] = im.clone()
+        if "nv" in fname:
+            kwargs["global_scale"] = calculate_gparam(w) * 0.9
+        qdq, scale, zp = Q[fname](w.clone(), **kwargs)
+        grp, _, _ = reshape_pad_tensor_by_group_size(w.clone(), kw["group_size"])
+        rec = {"w": w, "imatrix": im, "kw": {k_: v for k_, v in kw.items()}, "fn": fname, "qdq": qdq, "scale": scale,
+               "zp": zp if not isinstance(zp, torch.Tensor) else zp.clone(),
+               "global_scale": kwargs.get("global_scale")}
+        out[name] = rec
+        print(name, "qdq", tuple(qdq.shape), "scale", tuple(scale.shape), scale.dtype)
+    torch.save(out, os.path.join(GOLDEN, "opt_rtn.pt"))
+    print("opt_rtn.pt:", len(out), "cases")
+
+
 def main(argv):
     from oracle.ref_shim import import_reference
 
     import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
-    what = (set(argv) - {"rtn"}) or ({"qdq", "pack", "block"} if "rtn" not in argv else set())
+    what = (set(argv) - {"rtn"}) or ({"qdq", "pack", "block", "opt"} if "rtn" not in argv else set())
+    if "opt" in what:
+        gen_opt_rtn()
     if "qdq" in what:
         gen_qdq()
     if "pack" in what:
@@ -258,7 +306,7 @@ if __name__ == "__main__":
 # quantize_and_save(format="auto_round") on the tiny Llama -> every packed tensor of the checkpoint.
 # Deterministic (no tuning), so the B200 path must reproduce the packed integers bit-for-bit.
 # ---------------------------------------------------------------------------------------------
-def gen_rtn_export(tag, scheme_kwargs):
+def gen_rtn_export(tag, scheme_kwargs, opt=False):
     import json
     import tempfile
 
@@ -270,8 +318,23 @@ def gen_rtn_export(tag, scheme_kwargs):
     model = tiny_llama()
     init_state = {k: v.clone() for k, v in model.state_dict().items()}
     tokens = torch.randint(0, 128, (8, 16), generator=torch.Generator().manual_seed(1))
+    imatrices = {}
+    if opt:
+        # observe (not alter) the reference: record each layer's normalised importance matrix as the optimized-RTN
+        # quantizer sees it, so that the oracle / CUDA scale search can be checked layer by layer
+        from auto_round.algorithms.quantization.rtn.quantizer import OptimizedRTNQuantizer
+
+        orig_qb = OptimizedRTNQuantizer.quantize_block
+
+        def spy(self, block, *a, **k):
+            for _n, m in block.named_modules():
+                if hasattr(m, "imatrix") and hasattr(m, "global_name"):
+                    imatrices[m.global_name] = (m.imatrix / m.imatrix_cnt).detach().float().cpu().clone()
+            return orig_qb(self, block, *a, **k)
+
+        OptimizedRTNQuantizer.quantize_block = spy
     with tempfile.TemporaryDirectory() as d:
-        ar = AutoRound(model, tokenizer=DummyTokenizer(), iters=0, disable_opt_rtn=True, nsamples=8, seqlen=16, batch_size=4,
+        ar = AutoRound(model, tokenizer=DummyTokenizer(), iters=0, disable_opt_rtn=(None if opt else True), nsamples=8, seqlen=16, batch_size=4,
                        dataset=[tokens[:4], tokens[4:]], device_map="cpu", enable_torch_compile=False, seed=42,
                        **scheme_kwargs)
         _, folders = ar.quantize_and_save(d, format="auto_round")
@@ -284,9 +347,14 @@ def gen_rtn_export(tag, scheme_kwargs):
                         t = f.get_tensor(k)
                         tensors[k] = t.view(torch.uint8) if t.dtype == torch.float8_e4m3fn else t
         qcfg = json.load(open(os.path.join(d, "config.json")))["quantization_config"]
+    if opt:
+        OptimizedRTNQuantizer.quantize_block = orig_qb
     keep = {k: v for k, v in tensors.items() if ".layers." in k and "layernorm" not in k}
-    torch.save({"init_state": init_state, "tokens": tokens, "tensors": keep, "quantization_config": qcfg,
-                "scheme_kwargs": scheme_kwargs}, os.path.join(GOLDEN, f"rtn_export_{tag}.pt"))
+    rec = {"init_state": init_state, "tokens": tokens, "tensors": keep, "quantization_config": qcfg,
+           "scheme_kwargs": scheme_kwargs}
+    if opt:
+        rec["imatrix"] = imatrices
+    torch.save(rec, os.path.join(GOLDEN, f"rtn_export_{tag}.pt"))
     print(f"rtn_export_{tag}.pt: {len(keep)} tensors; config keys {sorted(qcfg)}")
 
 
@@ -298,3 +366,7 @@ if __name__ == "__main__" and "rtn" in sys.argv[1:]:
     gen_rtn_export("w2a16_asym_g32", dict(scheme="W2A16", group_size=32, sym=False))
     gen_rtn_export("nvfp4", dict(scheme="NVFP4", act_bits=16, act_data_type="float"))
     gen_rtn_export("mxfp4", dict(scheme="MXFP4", act_bits=16))
+    # optimized RTN (the reference's default for iters=0): imatrix from the calibration forward + scale search
+    gen_rtn_export("opt_w4a16_sym_g32", dict(scheme="W4A16", group_size=32), opt=True)
+    gen_rtn_export("opt_nvfp4", dict(scheme="NVFP4", act_bits=16, act_data_type="float"), opt=True)
+    gen_rtn_export("opt_mxfp4", dict(scheme="MXFP4", act_bits=16), opt=True)

@@ -280,5 +280,127 @@ def search_scales_int(g: torch.Tensor, bits: int, qw=None, search_ratio=0.75):
     return scales
 
 
+# --------------------------------------------------------------------------------------------
+# optimized RTN (iters == 0, disable_opt_rtn unset) -- the scale search weighted by the imatrix
+#   auto_round/data_type/int.py:89-122      opt_rtn_int_sym
+#   auto_round/data_type/nvfp.py:331-408    search_nvfp4_scale, opt_rtn_nv_fp4
+#   auto_round/data_type/mxfp.py:103-169    search_mx_scale (alg_ext init scale)
+#   auto_round/data_type/gguf.py:437-484    _imatrix_handle_zero
+# --------------------------------------------------------------------------------------------
+def imatrix_handle_zero(qw: torch.Tensor, g: torch.Tensor, bits: int, group_size: int):
+    """qw, g: [G,gs].  Groups whose importance holds zeros get a weight-derived or mean-filled importance."""
+    if torch.min(qw) != 0:
+        return qw
+    qw = qw.reshape(-1, qw.shape[-1]).clone()
+    zero_cnt = torch.sum(qw <= 1e-30, dim=-1)
+    replace = zero_cnt > group_size // 2
+    if torch.sum(replace) > 0:
+        if bits <= 3:
+            tmp = torch.abs(g)
+        else:
+            tmp = torch.abs(g) + torch.sqrt(torch.sum(torch.pow(g, 2), dim=-1, keepdim=True) / 32)
+        tmp = tmp.to(qw.dtype)
+        qw[replace, :] = tmp[replace, :]
+    mean_replace = (zero_cnt > 0) & (zero_cnt <= group_size // 2)
+    if torch.sum(mean_replace) > 0:
+        tmp = (torch.sum(qw, dim=-1) / (qw.shape[1] - zero_cnt)).view(-1, 1).expand(-1, qw.shape[1])
+        idx = qw == 0
+        qw[idx] = tmp[idx]
+    return qw.reshape(g.shape)
+
+
+def imatrix_weights(imatrix, g: torch.Tensor, bits: int, group_size: int):
+    """[K] importance -> [G,gs] per-element loss weights (int.py:107-115): pad K with 1e-5, broadcast over rows."""
+    if imatrix is None:
+        return 1.0
+    im = imatrix.reshape(1, -1)
+    k = im.shape[1]
+    if group_size > 0 and k >= group_size and k % group_size:
+        im = torch.nn.functional.pad(im, (0, math.ceil(k / group_size) * group_size - k), value=1e-5)
+    im = im.reshape(1, -1)
+    qw = im.expand(g.numel() // im.numel(), -1).reshape(g.shape)
+    return imatrix_handle_zero(qw, g, bits, group_size)
+
+
+def opt_rtn_int_sym(w, bits=4, group_size=128, imatrix=None, q_scale_thresh=1e-5):
+    """Returns (qdq, scale [G,1] in w.dtype, maxq).  All range math stays in the weight dtype (bf16)."""
+    g, shape, pad = to_groups(w, group_size)
+    maxq = int(2.0 ** (bits - 1))
+    qw = imatrix_weights(imatrix, g, bits, group_size)
+    scale = search_scales_int(g, bits, qw=qw)
+    scale = torch.where(scale < 0, torch.clamp(scale, max=-q_scale_thresh), torch.clamp(scale, min=q_scale_thresh))
+    q = g.div(scale).round_().clamp_(-maxq, maxq - 1)
+    out = q.mul_(scale).to(g.dtype)
+    return from_groups(out, shape, pad), scale, maxq
+
+
+def search_scales_nvfp4(g: torch.Tensor, qw=1.0):
+    """[G,16] -> best per-group coefficient in {1.0, 0.50 .. 1.51} (nvfp.py:331-385).  The search derives its own
+    per-tensor global scale from `g` (global_scale=None inside), NOT the layer's fused one."""
+    x = g.float()
+    q0, scale, _ = nv_fp4(x, group_size=16, v=0, max_scale=1.0)
+    best = (((q0 - x) ** 2) * qw).sum(dim=-1)
+    best_scale = torch.ones_like(scale)
+    for sv in range(50, 152):
+        c = sv / 100.0
+        if c == 1.0:
+            continue
+        test = torch.full_like(scale, c)
+        q, _, _ = nv_fp4(x, group_size=16, v=0, max_scale=test)
+        loss = (((q - x) ** 2) * qw).sum(dim=-1)
+        m = loss < best
+        best[m] = loss[m]
+        best_scale[m.view(-1, 1) if best_scale.dim() == 2 else m] = c
+    return best_scale
+
+
+def opt_rtn_nv_fp4(w, group_size=16, global_scale=None, max_scale=1.0, imatrix=None):
+    g, shape, pad = to_groups(w, group_size)
+    qw = imatrix_weights(imatrix, g, 4, group_size) if isinstance(imatrix, torch.Tensor) else 1.0
+    init_scale = search_scales_nvfp4(g, qw)
+    return nv_fp4(w, group_size=group_size, v=0, global_scale=global_scale, max_scale=max_scale, init_scale=init_scale) + (init_scale,)
+
+
+def _qdq_mxfp_given_max(x, max_val, emax=2, max_norm=6.0):
+    """mxfp.py:172-199 (qdq_mxfp): shared exponent from a GIVEN per-group max."""
+    shared_exp = torch.where(max_val == 0, torch.ones_like(max_val), torch.log2(max_val))
+    shared_exp = torch.floor(shared_exp) - emax
+    shared_exp = torch.clamp(shared_exp, min=-127.0, max=127.0)
+    t = x / (2 ** shared_exp)
+    t = torch.clamp(t, min=-max_norm, max=max_norm)
+    t = mx_quant_element(t)
+    return t * (2 ** shared_exp)
+
+
+def search_scales_mx(g: torch.Tensor, qw=None):
+    """[G,32] -> per-group coefficient in {1, 0.5, 2} (mxfp.py:103-169)."""
+    x = g.to(torch.float32)
+    max_val, _ = torch.max(torch.abs(x), dim=-1, keepdim=True)
+    scales = torch.ones_like(max_val)
+
+    def loss_of(q):
+        e = (q - x).pow(2)
+        if isinstance(qw, torch.Tensor) or (qw is not None and qw != 1.0):
+            e = e * qw
+        return e.sum(dim=-1)
+
+    best = loss_of(_qdq_mxfp_given_max(x, max_val))
+    for c in (0.5, 2.0):
+        loss = loss_of(_qdq_mxfp_given_max(x, max_val * c))
+        m = loss < best
+        scales[m] = c
+        best[m] = loss[m]
+    return scales
+
+
+def opt_rtn_mx_fp4(w, group_size=32, imatrix=None):
+    """mxfp.py:172-230 (quant_mx_opt_rtn): the {0.5,1,2} coefficient search, then the plain shared-exponent qdq."""
+    g, _, _ = to_groups(w, group_size)
+    qw = imatrix_weights(imatrix, g.to(torch.float32), 4, group_size) if isinstance(imatrix, torch.Tensor) else None
+    coeff = search_scales_mx(g, qw)
+    return mx_fp4(w, group_size=group_size, max_scale=coeff.view(-1)) + (coeff,)
+
+
 # name -> function, mirrors the registry lookup the reference does in data_type/utils.py:105-176
-QDQ = {"int_sym": int_sym, "int_asym": int_asym, "rtn_int_sym": rtn_int_sym, "mx_fp4": mx_fp4, "nv_fp4": nv_fp4}
+QDQ = {"int_sym": int_sym, "int_asym": int_asym, "rtn_int_sym": rtn_int_sym, "mx_fp4": mx_fp4, "nv_fp4": nv_fp4,
+       "opt_rtn_int_sym": opt_rtn_int_sym, "opt_rtn_nv_fp4": opt_rtn_nv_fp4, "opt_rtn_mx_fp4": opt_rtn_mx_fp4}
