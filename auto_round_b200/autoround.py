@@ -580,7 +580,10 @@ class AutoRound:
             self._hook(bi, "d2h0")
             block.to("cpu")
             self._hook(bi, "done")
-            self.block_results.append({"block": f"{prefix}.{bi}", "imatrix_layers": len(imatrices)})
+            rec = {"block": f"{prefix}.{bi}", "imatrix_layers": len(imatrices)}
+            if getattr(self, "keep_imatrix", False):           # inspection hook for the parity tests
+                rec["imatrix"] = {n: (None if t is None else t.detach().cpu()) for n, t in imatrices.items()}
+            self.block_results.append(rec)
         torch.cuda.synchronize(self.device)
         self.timings["tuning_s"] = time.time() - t0
         self.quantized, self._packed = True, self._pack_on_the_fly

@@ -110,23 +110,68 @@ KW = {"opt_w4a16_sym_g32": dict(scheme="W4A16", group_size=32), "opt_nvfp4": dic
       "opt_mxfp4": dict(scheme="MXFP4", act_bits=16)}
 
 
-@pytest.mark.parametrize("tag", list(KW))
-def test_default_rtn_checkpoint_matches_reference(golden_dir, tag, tmp_path):
-    """`AutoRound(iters=0)` with the reference's default routing (calibrated imatrix search for int sym and NVFP4, zero-shot
-    search for MXFP4) must reproduce the reference's checkpoint: names, dtypes, shapes and config exactly; packed values
-    bit-exact up to near-tie groups (<= 2 % of the bytes of any tensor; 0 expected)."""
-    from safetensors import safe_open
+def _tiny_llama(state):
     from transformers import LlamaConfig, LlamaForCausalLM
 
-    rec = torch.load(os.path.join(golden_dir, f"rtn_export_{tag}.pt"), weights_only=False)
     cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
                       num_key_value_heads=2, vocab_size=128, max_position_embeddings=64, rms_norm_eps=1e-5,
                       rope_theta=10000.0, tie_word_embeddings=False)
     model = LlamaForCausalLM(cfg).to(torch.bfloat16).eval()
-    model.load_state_dict(rec["init_state"])
+    model.load_state_dict(state)
+    return model
+
+
+@pytest.mark.parametrize("tag", list(KW))
+def test_opt_rtn_layers_bit_exact_given_reference_imatrix(golden_dir, tag):
+    """Layer by layer, with the importance matrix the REFERENCE collected (recorded in the fixture; None for MXFP4):
+    search -> qdq -> pack must reproduce every packed tensor of the reference's checkpoint bit for bit."""
+    from auto_round_b200 import export
+    from auto_round_b200.quantizer import SignRoundQuantizer
+    from auto_round_b200.schemes import parse_scheme
+
+    rec = torch.load(os.path.join(golden_dir, f"rtn_export_{tag}.pt"), weights_only=False)
+    model = _tiny_llama(rec["init_state"])
+    kw = dict(KW[tag])
+    scheme = parse_scheme(kw.pop("scheme"), kw)
+    quantizer = SignRoundQuantizer(scheme, iters=0, batch_size=4)
+    for li, block in enumerate(model.model.layers):
+        block.to(DEV)
+        names = [n for n, m in block.named_modules() if quantizer.layer_filter(n, m)]
+        assert len(names) == 7
+        nv_gs = AutoRound._fuse_nv_global_scales(block, names) if scheme.qdq_name == "nv_fp4" else None
+        imx = {n: (rec["imatrix"][f"model.layers.{li}.{n}"].to(DEV) if rec["imatrix"] else None) for n in names}
+        done = quantizer.rtn_block(block, None, nv_gs, imatrices=imx)
+        for n in done:
+            ql = export.pack_linear(block.get_submodule(n), scheme, DEV)
+            for key, ref in rec["tensors"].items():
+                base, leaf = key.rsplit(".", 1)
+                if base != f"model.layers.{li}.{n}":
+                    continue
+                got = getattr(ql, leaf)
+                got = got.view(torch.uint8) if got.dtype == torch.float8_e4m3fn else got
+                assert got.dtype == ref.dtype and tuple(got.shape) == tuple(ref.shape), key
+                assert torch.equal(got.cpu(), ref), key
+        block.to("cpu")
+
+
+@pytest.mark.parametrize("tag", list(KW))
+def test_default_rtn_checkpoint_matches_reference(golden_dir, tag, tmp_path):
+    """`AutoRound(iters=0)` end to end with the reference's default routing (calibrated imatrix search for int sym and
+    NVFP4, zero-shot search for MXFP4): tensor names, dtypes, shapes and quantization_config exactly.  Values: MXFP4 (no
+    calibration) bit-exact.  For the calibrated routes the importance matrix comes from OUR bf16 block forward on the GPU,
+    the fixture's from the reference's CPU forward; activations differ in the last bf16 bit, the imatrix by ~1e-3, and the
+    argmin over 200 near-flat candidates then moves for a few percent of the groups (the reference's own CPU and CUDA runs
+    differ the same way).  `reference_mask_cast=True` reproduces the reference's bf16 cast of the boolean attention mask
+    (autoround.py:199-203).  Checked: imatrix within 5 % of the recorded one, and < 2 % of any tensor's bytes differ (measured 0.2 %); the
+    bit-exact statement is test_opt_rtn_layers_bit_exact_given_reference_imatrix above."""
+    from safetensors import safe_open
+
+    rec = torch.load(os.path.join(golden_dir, f"rtn_export_{tag}.pt"), weights_only=False)
+    model = _tiny_llama(rec["init_state"])
     tokens = rec["tokens"]
     ar = AutoRound(model, tokenizer=_Tok(), iters=0, nsamples=8, seqlen=16, batch_size=4, dataset=[tokens[:4], tokens[4:]],
-                   device_map=0, seed=42, **KW[tag])
+                   device_map=0, seed=42, reference_mask_cast=True, **KW[tag])
+    ar.keep_imatrix = True
     assert ar._rtn_mode() == ("zero_shot_opt" if tag == "opt_mxfp4" else "calibrated_opt")
     out = str(tmp_path / "ckpt")
     ar.quantize_and_save(out, format="auto_round")
@@ -142,10 +187,20 @@ def test_default_rtn_checkpoint_matches_reference(golden_dir, tag, tmp_path):
         a, b = got[k].contiguous().view(torch.uint8).reshape(-1), ref.contiguous().view(torch.uint8).reshape(-1)
         frac = (a != b).float().mean().item()
         worst = max(worst, frac)
-        assert frac <= 0.02, (k, frac)
+        assert frac <= (0.0 if tag == "opt_mxfp4" else 0.02), (k, frac)      # measured on B200: 0.00195
     print(f"{tag}: worst mismatching byte fraction {worst:.5f}")
+    extra = {k for k in got if ".layers." in k and "layernorm" not in k} - set(rec["tensors"])
+    assert not extra, extra
     qc = json.load(open(os.path.join(out, "config.json")))["quantization_config"]
     assert qc == rec["quantization_config"]
+    if tag != "opt_mxfp4":
+        seen = 0
+        for res in ar.block_results:
+            for n, t in res["imatrix"].items():
+                ref = rec["imatrix"][f"{res['block']}.{n}"]
+                assert torch.allclose(t, ref, rtol=5e-2, atol=1e-6), (res["block"], n, (t - ref).abs().max().item())
+                seen += 1
+        assert seen == 14
 
 
 def test_rtn_routing_mirrors_reference():

@@ -48,4 +48,34 @@ for rep in range(2):          # rep 0 = warm, rep 1 = the launch to read in the 
     wq2, scale, _ = ops.qdq_fwd(spec, w, v, mn, mx, wmin, wmax, None, want_scale=True)
     ops.pack_int(wq2, scale.reshape(n, -1).contiguous(), None, 4, 128, True, zp_const=8)
 torch.cuda.synchronize()
+
+# optimized-RTN kernels at the same layer: importance accumulation over one batch of tokens and the
+# 201-candidate scale search; CUDA-event timings printed so that a plain run doubles as the measurement
+imx = torch.zeros(k, dtype=torch.float32, device=dev)
+nv = ops.make_spec("nv_fp4", 4, 16, n, k)
+mxs = ops.make_spec("mx_fp4", 4, 32, n, k)
+
+
+def timed(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+t_im = timed(lambda: ops.imatrix_accum(x, imx))
+qw = imx / 8.0 + 1e-3
+t_int = timed(lambda: ops.search_scale_int(spec, w, qw))
+t_nv = timed(lambda: ops.search_scale_nv(nv, w, qw))
+t_mx = timed(lambda: ops.search_scale_mx(mxs, w, qw))
+cand = len(ops.int_search_table(4))
+print("imatrix_accum  [%d x %d] bf16: %.3f ms = %.2f TB/s" % (T, k, t_im, T * k * 2 / t_im / 1e9))
+print("search_scale_int W4 g128 [%d x %d], %d candidates: %.3f ms = %.1f G candidate-weights/s" % (n, k, cand, t_int, n * k * cand / t_int / 1e6))
+print("search_scale_nv  g16, %d candidates (+ absmax pass): %.3f ms" % (len(ops.NV_SEARCH_TABLE), t_nv))
+print("search_scale_mx  g32, 3 candidates: %.3f ms" % t_mx)
 print("done")
