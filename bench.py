@@ -316,7 +316,12 @@ def gemm_roofline(dev, pk):
             "achieved": round(achieved, 1), "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops"], 4),
             "peak_source": pk["source"], "traffic": None, "flops_per_launch": flops // nlaunch,
             "avg_launch_ms": round(ms / nlaunch, 4), "launches_per_iteration": nlaunch,
-            "how": "18 GEMM launches of one iteration replayed x10 after 3 warm-ups; operands 3.4 GB >> L2"}
+            "how": "18 GEMM launches of one iteration replayed x10 after 3 warm-ups; operands 3.4 GB >> L2",
+            # dram read+write per launch from the one `ncu --set full` capture on file (gate/up_proj shape, 1.92e12 FLOP):
+            # the mix above averages over 7 layer shapes, for which no per-launch capture exists, hence traffic = null
+            "traffic_ncu_gate_proj_bytes": {"fwd": 1668550800, "grad_in": 2475847704, "grad_w_fused": 3952551056,
+                                            "algorithmic": {"fwd": 721420288, "grad_in": 721420288, "grad_w_fused": 1191182336},
+                                            "source": "profiles/r01_ncu_prof_gemm2.md"}}
 
 
 def cpu_baseline(budget_s: float = 25.0, threads=None):
