@@ -57,6 +57,15 @@ def _worker(rank, world, port, out):
         ps = [torch.zeros_like(p) for _ in range(world)]
         dist.all_gather(ps, p)
         assert all(torch.equal(ps[0], q) for q in ps)
+        # optimized RTN under DP: each rank accumulates sum x^2 and the sample count over ITS shard of the calibration
+        # forward; one all-reduce of (sum, count) gives every rank the reference's normalised importance matrix
+        xs = torch.randn(16, 5, 32, generator=torch.Generator().manual_seed(11))
+        per = 16 // world
+        part = xs[rank * per:(rank + 1) * per]
+        acc, cnt = part.reshape(-1, 32).pow(2).sum(0), torch.tensor([float(part.shape[0])])
+        dp.all_reduce_(acc, cnt)
+        assert float(cnt) == 16.0
+        assert torch.allclose(acc / cnt, xs.reshape(-1, 32).pow(2).sum(0) / 16, rtol=1e-6)
         out.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         out.put((rank, repr(e)))
