@@ -196,7 +196,10 @@ def gen_block(tag, scheme_kwargs, iters=8, nsamples=8, seqlen=16, batch_size=4):
                    input_ids=detach_tree(input_ids), batches=[], losses=[],
                    block_state={k: v.clone() for k, v in block.state_dict().items()},
                    nv_gs={n: m.weight_global_scale.clone() for n, m in block.named_modules()
-                          if hasattr(m, "weight_global_scale")})
+                          if hasattr(m, "weight_global_scale")},
+                   # enable_alg_ext: the (unnormalised) importance matrix each layer holds when the tuner starts
+                   imatrix={n: m.imatrix.detach().float().clone() for n, m in block.named_modules()
+                            if isinstance(getattr(m, "imatrix", None), torch.Tensor)})
         r = orig_qb(self, block, fp_inputs, input_others, fp_outputs, q_inputs, block_ctx, input_ids=input_ids, **kw)
         layers = {}
         for n, m in block.named_modules():
@@ -295,6 +298,12 @@ def main(argv):
         gen_block("w2a16_asym_g32", dict(scheme="W2A16", group_size=32, sym=False))
         gen_block("nvfp4", dict(scheme="NVFP4", act_bits=16, act_data_type="float"))
         gen_block("mxfp4", dict(scheme="MXFP4", act_bits=16))
+    if "algext" in what:
+        # enable_alg_ext (sign_roundv2): searched init_scale, max_scale in [0,2]; outlier-masked loss when bits < 4
+        gen_block("algext_w2a16_sym_g32", dict(scheme="W2A16", group_size=32, enable_alg_ext=True))
+        gen_block("algext_w4a16_sym_g32", dict(scheme="W4A16", group_size=32, enable_alg_ext=True))
+        gen_block("algext_mxfp4", dict(scheme="MXFP4", act_bits=16, enable_alg_ext=True))
+        gen_block("algext_nvfp4", dict(scheme="NVFP4", act_bits=16, act_data_type="float", enable_alg_ext=True))
 
 
 if __name__ == "__main__":

@@ -221,6 +221,10 @@ def nv_fp4(w, group_size=16, v=0, global_scale=None, max_scale=1.0, init_scale=1
     if global_scale is None:
         global_scale = nv_global_scale(g)
     gs = global_scale.to(torch.float32)
+    if isinstance(max_scale, torch.Tensor):
+        max_scale = max_scale.view(-1)
+    if isinstance(init_scale, torch.Tensor):
+        init_scale = init_scale.view(-1)
     coeff = max_scale * init_scale
     if isinstance(coeff, torch.Tensor):
         coeff = coeff.view(-1, 1)

@@ -73,9 +73,11 @@ class ReplaySampler:
 class TunableLinear(nn.Module):
     """WrapperLinear restated: same parameters, same per-forward in-place clamp, same qdq call."""
 
-    def __init__(self, linear: nn.Linear, scheme: LayerScheme, global_scale=None, minmax_bound=(0.0, 1.0)):
+    def __init__(self, linear: nn.Linear, scheme: LayerScheme, global_scale=None, minmax_bound=(0.0, 1.0),
+                 init_scale=None):
         super().__init__()
         self.linear, self.scheme, self.bound = linear, scheme, minmax_bound
+        self.init_scale = init_scale          # alg_ext (SignRoundOptimizedWrapperLinear): searched per-group init scale
         w = linear.weight.data
         groups, _, _ = Q.to_groups(w, scheme.group_size)
         self.wmin = torch.clamp(groups.min(1)[0], max=0)
@@ -98,14 +100,15 @@ class TunableLinear(nn.Module):
         name = sc.qdq_name
         if name == "int_sym":
             out = Q.int_sym(w, sc.bits, sc.group_size, value, min_scale, max_scale, self.wmin, self.wmax,
-                            sc.scale_dtype, self.q_scale_thresh)
+                            sc.scale_dtype, self.q_scale_thresh, init_scale=self.init_scale)
         elif name == "int_asym":
             out = Q.int_asym(w, sc.bits, sc.group_size, value, min_scale, max_scale, self.wmin, self.wmax,
                              sc.scale_dtype, self.q_scale_thresh)
         elif name == "mx_fp4":
-            out = Q.mx_fp4(w, sc.group_size, value, max_scale)
+            out = Q.mx_fp4(w, sc.group_size, value, max_scale, init_scale=self.init_scale)
         else:
-            out = Q.nv_fp4(w, sc.group_size, value, self.global_scale, max_scale)
+            out = Q.nv_fp4(w, sc.group_size, value, self.global_scale, max_scale,
+                           init_scale=1.0 if self.init_scale is None else self.init_scale)
         wq, scale, zp = out
         return wq.to(w.dtype), scale, zp
 
@@ -134,8 +137,50 @@ class TunableLinear(nn.Module):
         return lin
 
 
-def wrap_block(block: nn.Module, scheme_of, nv_global_scales=None):
-    """wrapper_block (wrapper.py:774-828): every nn.Linear with bits <= 8 -> TunableLinear."""
+def search_init_scale(w, scheme: LayerScheme, imatrix=None, q_scale_thresh=1e-5):
+    """search_optimized_init_scale (data_type/utils.py:223-254) on the grouped weight; the importance matrix is padded with
+    1e-5 and broadcast over rows WITHOUT the zero repair of the RTN route (reshape_imatrix_for_weight, :269-282)."""
+    g, _, _ = Q.to_groups(w, scheme.group_size)
+    if imatrix is None:
+        qw = torch.ones_like(g)
+    else:
+        im = imatrix.reshape(1, -1)
+        k = im.shape[1]
+        gs = scheme.group_size
+        if gs > 0 and k >= gs and k % gs:
+            im = F.pad(im, (0, (k + gs - 1) // gs * gs - k), value=1e-5)
+        qw = im.reshape(1, -1).expand(g.numel() // im.numel(), -1).reshape(g.shape)
+    name = scheme.qdq_name
+    if name == "int_sym":
+        s0 = Q.search_scales_int(g, scheme.bits, qw)
+        return torch.where(s0 < 0, torch.clamp(s0, max=-q_scale_thresh), torch.clamp(s0, min=q_scale_thresh))
+    if name == "mx_fp4":
+        return Q.search_scales_mx(g, qw)
+    if name == "nv_fp4":
+        return Q.search_scales_nvfp4(g, qw)
+    return None                                   # int asym keeps the plain wrapper (data_type/utils.py:197-201)
+
+
+def outlier_suppressed_loss(pred, ref, mask):
+    """SignRoundV2Quantizer._get_loss (sign_roundv2/quantizer.py:362-399): the numel/1000 largest |pred - ref| (taken on
+    the bf16 difference, token mask NOT applied to the selection) are zeroed, then mean over ALL elements of the squared
+    fp32 difference."""
+    diff = torch.abs(pred - ref)
+    flat = diff.view(-1)
+    topk = max(1, int(flat.numel() / 1000))
+    _, top = torch.topk(torch.abs(flat), topk)
+    keep = torch.ones_like(flat, dtype=torch.bool)
+    keep[top] = False
+    keep = keep.view_as(diff)
+    d = torch.abs(pred.to(torch.float32) - ref.to(torch.float32))
+    if mask is not None:
+        return torch.mean((d * mask * keep) ** 2)
+    return torch.mean((d * keep) ** 2)
+
+
+def wrap_block(block: nn.Module, scheme_of, nv_global_scales=None, alg_ext=False, imatrices=None):
+    """wrapper_block (wrapper.py:774-828): every nn.Linear with bits <= 8 -> TunableLinear.  alg_ext: symmetric int / mx /
+    nv layers get the optimized wrapper (searched init_scale, max_scale bound [0,2]; sign_roundv2/quantizer.py:101-125)."""
     wrapped = {}
     for name, mod in list(block.named_modules()):
         if type(mod) is nn.Linear:
@@ -143,7 +188,12 @@ def wrap_block(block: nn.Module, scheme_of, nv_global_scales=None):
             if sc is None or sc.bits > 8:
                 continue
             gs = None if nv_global_scales is None else nv_global_scales.get(name)
-            tl = TunableLinear(mod, sc, gs)
+            init, bound = None, (0.0, 1.0)
+            if alg_ext and sc.qdq_name != "int_asym":
+                thr = 1e-8 if sc.scale_dtype == torch.float32 else 1e-5
+                init = search_init_scale(mod.weight.data, sc, (imatrices or {}).get(name), thr)
+                bound = (0.0, 2.0)
+            tl = TunableLinear(mod, sc, gs, bound, init)
             parent = block
             parts = name.split(".")
             for p in parts[:-1]:
@@ -218,11 +268,13 @@ class TuneResult:
 
 def tune_block(block, inputs, others, fp_outputs, scheme_of, iters=200, batch_size=8, lr=None, minmax_lr=None,
                token_masks=None, enable_minmax_tuning=True, nv_global_scales=None, amp=True,
-               not_use_best_mse=False, sampler=None) -> TuneResult:
+               not_use_best_mse=False, sampler=None, alg_ext=False, imatrices=None, outlier_loss=None) -> TuneResult:
     """quantize_block: `inputs`/`fp_outputs` are per-sample lists of [1,S,H]; `token_masks` per-sample [1,S]
     long tensors (1 = valid) or None.  Mutates `block` in place (qdq weights + scale/zp attributes)."""
     nsamples = len(inputs)
-    wrapped = wrap_block(block, scheme_of, nv_global_scales)
+    wrapped = wrap_block(block, scheme_of, nv_global_scales, alg_ext, imatrices)
+    if outlier_loss is None:   # sign_roundv2/quantizer.py:334-352: symmetric schemes with bits < 4 (act quant is out of scope)
+        outlier_loss = alg_ext and any(tl.init_scale is not None and tl.scheme.bits < 4 for tl in wrapped.values())
     res = TuneResult()
     if not wrapped:
         return res
@@ -259,7 +311,14 @@ def tune_block(block, inputs, others, fp_outputs, scheme_of, iters=200, batch_si
         ref = torch.cat([fp_outputs[i] for i in idx], dim=0)
         x, sel = select_batch(inputs, others, idx)
         pred = block_forward(block, x, sel, amp)
-        loss = masked_mse(pred, ref, mask)
+        if outlier_loss:
+            loss = outlier_suppressed_loss(pred, ref, mask)
+        elif alg_ext:
+            # SignRoundV2Quantizer._get_loss falls back to super()._get_loss WITHOUT forwarding valid_token_mask
+            # (sign_roundv2/quantizer.py:399): plain MSE over every token; num_elm below still counts valid tokens only
+            loss = masked_mse(pred, ref, None)
+        else:
+            loss = masked_mse(pred, ref, mask)
         num_elm = 1 if num_elm <= 0 else num_elm
         total = loss.item() / num_elm
         (loss * 1000).backward()

@@ -168,6 +168,35 @@ def test_tune_block_matches_reference_bit_exact(golden_dir, tag):
                 assert torch.equal(mod.zp.reshape(-1), lay["zp"].reshape(-1)), (tag, name)
 
 
+ALGEXT = {
+    "algext_w2a16_sym_g32": S.LayerScheme(2, 32, True, "int"),      # init scale + outlier-masked loss
+    "algext_w4a16_sym_g32": S.LayerScheme(4, 32, True, "int"),      # init scale only
+    "algext_mxfp4": S.LayerScheme(4, 32, True, "mx_fp"),
+    "algext_nvfp4": S.LayerScheme(4, 16, True, "nv_fp"),
+}
+
+
+@pytest.mark.parametrize("tag", list(ALGEXT))
+def test_tune_block_alg_ext_matches_reference_bit_exact(golden_dir, tag):
+    """enable_alg_ext=True (sign_roundv2): searched init_scale, max_scale in [0,2], outlier-masked loss for bits < 4."""
+    rec = _load(golden_dir, f"block_{tag}.pt")
+    sc = ALGEXT[tag]
+    for b in rec["blocks"]:
+        assert len(b["imatrix"]) == 7
+        blk = _tiny_block(b["block_state"])
+        masks = [(ids != -100).to(torch.long) for ids in b["input_ids"]]
+        res = S.tune_block(blk, b["inputs"], b["others"], b["fp_outputs"], lambda n, m: sc, iters=rec["iters"],
+                           batch_size=rec["batch_size"], token_masks=masks, nv_global_scales=b["nv_gs"] or None,
+                           sampler=S.ReplaySampler(b["batches"]), alg_ext=True, imatrices=b["imatrix"])
+        nvalid = [sum(int(masks[i].sum()) for i in batch) for batch in b["batches"]]
+        got = [l * n for l, n in zip(res.losses, nvalid)]
+        assert got == pytest.approx(b["losses"], rel=1e-6)
+        for name, lay in b["layers"].items():
+            mod = blk.get_submodule(name)
+            assert torch.equal(mod.weight.data, lay["weight"]), (tag, name)
+            assert torch.equal(mod.scale.float().reshape(-1), lay["scale"].float().reshape(-1)), (tag, name)
+
+
 def test_index_sampler_is_python_random():
     import random
 
