@@ -15,7 +15,8 @@ DT_INT_SYM, DT_INT_ASYM, DT_MX_FP4, DT_NV_FP4 = 0, 1, 2, 3
 
 class QSpec(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("bits", C.c_int32), ("group_size", C.c_int32), ("n", C.c_int32),
-                ("k", C.c_int32), ("q_scale_thresh", C.c_float), ("scale_bound_hi", C.c_float)]
+                ("k", C.c_int32), ("q_scale_thresh", C.c_float), ("scale_bound_hi", C.c_float),
+                ("init_scale", C.c_void_p)]          # device fp32 [G] or NULL (enable_alg_ext)
 
 
 _P, _I, _L, _F, _D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
@@ -56,6 +57,9 @@ SIGNATURES = {
     "ar_search_scale_nv": [_P, _P, _L, _P, _P, _I, _QS, _P, _P],
     "ar_search_scale_mx": [_P, _P, _L, _P, _I, _QS, _P, _P],
     "ar_imatrix_accum": [_P, _L, _I, _P, _P],
+    "ar_absdiff_hist": [_P, _P, _L, _P, _P],
+    "ar_topk_threshold": [_P, _L, _P, _P],
+    "ar_mse_outlier_fwd_bwd": [_P, _P, _P, _L, _L, _F, _P, _P, _P, _P],
 }
 
 _lib = None

@@ -12,6 +12,7 @@ AutoScheme, MLLM / diffusion calibration, torch.compile, CPU execution.
 """
 from __future__ import annotations
 
+import os
 import random
 import time
 from typing import Optional
@@ -181,9 +182,14 @@ class AutoRound:
         self.model = model.eval()
         self.tokenizer = tokenizer
         self.scheme: QuantizationScheme = parse_scheme(scheme, {k: kwargs.get(k) for k in _SCHEME_KW})
-        if kwargs.get("enable_alg_ext") and self.scheme.qdq_name != "int_asym":
-            raise NotImplementedError("enable_alg_ext: only the int-asym case (where the reference keeps the plain "
-                                      "WrapperLinear, sign_roundv2/quantizer.py:334-357) is in scope this round")
+        # enable_alg_ext (sign_roundv2): int asym keeps the plain wrapper in the reference (sign_roundv2/quantizer.py:334-357).
+        # The symmetric route (searched init scale, max_scale in [0,2], outlier-suppressed loss) is written and pinned on the
+        # CPU side (oracle + tests/golden/block_algext_*.pt) but its CUDA path has not run on hardware yet, so it has to be
+        # asked for explicitly; without the switch the request fails loudly instead of running unvalidated numerics.
+        self.enable_alg_ext = bool(kwargs.get("enable_alg_ext")) and self.scheme.qdq_name != "int_asym"
+        if self.enable_alg_ext and os.environ.get("AR_B200_UNVERIFIED", "0") != "1":
+            raise NotImplementedError("enable_alg_ext for symmetric schemes: CUDA path not yet validated on a B200 "
+                                      "(set AR_B200_UNVERIFIED=1 to run it; tests/test_gpu_alg_ext.py holds its parity tests)")
         self.layer_config = layer_config or {}
         self.dataset = dataset
         self.iters = 200 if iters is None else int(iters)
@@ -430,7 +436,8 @@ class AutoRound:
         token_masks = [m.to(self.device) for m in token_masks_cpu] if any_masked else None
 
         quantizer = SignRoundQuantizer(self.scheme, iters=self.iters, batch_size=self.batch_size, amp_dtype=self.amp_dtype,
-                                       layer_config=self.layer_config, dp=self.dp, **self.sign_kw)
+                                       layer_config=self.layer_config, dp=self.dp, enable_alg_ext=self.enable_alg_ext,
+                                       **self.sign_kw)
         self.quantizer = quantizer
         t0 = time.time()                                                  # orchestrator.py:631
         q_inputs = None
@@ -450,12 +457,18 @@ class AutoRound:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             ev[0].record()
             # (3) reference outputs of the FP block on the FP inputs  (composer.py:423-429)
-            ref_out = self._forward_all(quantizer, block, fp_inputs, others, token_masks)
+            imatrices = None
+            if self.enable_alg_ext:     # imatrix hooks on the FP-input forward, raw sums (sign_roundv2/quantizer.py:401-428)
+                with _collect_imatrix(block, names, self.device) as col:
+                    ref_out = self._forward_all(quantizer, block, fp_inputs, others, token_masks)
+                imatrices = col.finish(self.dp, normalise=False)
+            else:
+                ref_out = self._forward_all(quantizer, block, fp_inputs, others, token_masks)
             ev[1].record()
             nv_gs = self._fuse_nv_global_scales(block, names) if self.scheme.qdq_name == "nv_fp4" else None
             eff = q_inputs if (q_inputs is not None and quantizer.enable_quanted_input) else fp_inputs
             quantizer.quantize_block(block, eff, others, ref_out, q_inputs, None, input_ids=ids_cache,
-                                     nv_global_scales=nv_gs)
+                                     nv_global_scales=nv_gs, imatrices=imatrices)
             res = quantizer.last_result
             ev[2].record()
             # (6) outputs of the quantised block feed the next block (composer.py:476-481)

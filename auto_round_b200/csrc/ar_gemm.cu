@@ -232,6 +232,7 @@ struct DwParams {                 // EPI_DW: fake-quant backward inputs/outputs
   float thr;
   int accumulate;
   int dv_bf16;
+  const float* init;              // ar_qspec::init_scale (alg_ext) or null
 };
 
 struct GemmParams {
@@ -335,6 +336,8 @@ __device__ __forceinline__ void epilogue_dw(const GemmParams& p, uint32_t tmem_a
       if ((kk % G) == 0) {                         // group starts here: build its context
         gi.mn = d.mn ? d.mn[gidx] : 1.f;
         gi.mx = d.mx ? d.mx[gidx] : 1.f;
+        gi.has_init = (d.init != nullptr);
+        gi.init = d.init ? d.init[gidx] : 1.f;
         if (IS_FP4) {
           float am = 0.f;
 #pragma unroll
@@ -752,7 +755,7 @@ extern "C" int ar_fq_linear_bwd_dw(const ar_qspec* q, const void* dy, const void
   AR_REQUIRE(q->dtype != AR_DT_NV_FP4 || gscale, AR_E_BADARG, "nv_fp4 needs gscale");
   GemmParams p{};
   p.dw = DwParams{(const uint16_t*)w, v, mn, mx, (const uint16_t*)wmin, (const uint16_t*)wmax, gscale, dv, dmin, dmax,
-                  q->bits, q->q_scale_thresh, accumulate, dv_bf16};
+                  q->bits, q->q_scale_thresh, accumulate, dv_bf16, q->init_scale};
   cudaStream_t st = (cudaStream_t)stream;
   // D[N_out, K_out] = sum_t dY[t,n] X[t,k]:  A = dY stored [T,N] (MN-major), B = X stored [T,K] (MN-major)
 #define AR_DW(CTX, GG, FP4) \

@@ -18,6 +18,7 @@ struct QArgs {
   const float* gscale;
   int n, k, kpad, bits;
   float thr;
+  const float* init;   // ar_qspec::init_scale (alg_ext) or null
 };
 
 template <int LPG>
@@ -71,6 +72,8 @@ __device__ __forceinline__ void make_group(const QArgs& a, int64_t gidx, const f
   gi.gscale = (IS_FP4 && a.gscale) ? *a.gscale : 0.f;
   gi.mn = (valid && a.mn) ? a.mn[gidx] : 1.f;
   gi.mx = (valid && a.mx) ? a.mx[gidx] : 1.f;
+  gi.has_init = (a.init != nullptr);
+  gi.init = (valid && a.init) ? a.init[gidx] : 1.f;
   if (IS_FP4) {
     float m = 0.f;
 #pragma unroll
@@ -256,6 +259,7 @@ static QArgs make_args(const ar_qspec* q, const void* w, const float* v, const f
   a.kpad = (q->k + q->group_size - 1) / q->group_size * q->group_size;
   a.thr = q->q_scale_thresh;
   a.bits = q->bits;
+  a.init = q->init_scale;
   return a;
 }
 

@@ -24,6 +24,8 @@ struct GroupIn {
   float thr;         // q_scale_thresh
   bool plain = false;  // no min/max_scale tensors (RTN, iters == 0): the reference's range math then stays in the
                        // weight dtype (bf16) because 0-dim / python scales do not promote (int.py:278-286)
+  float init = 1.f;    // enable_alg_ext: searched initial scale of the group (ar_qspec::init_scale)
+  bool has_init = false;
 };
 
 struct GroupAcc {
@@ -41,6 +43,16 @@ struct IntSym {
 
   __device__ __forceinline__ void init(int bits) { kMaxq = (float)(1 << (bits - 1)); }
   __device__ __forceinline__ void setup(const GroupIn& g) {
+    if (g.has_init) {                                  // int.py:201-216: scale = fp16(init_scale * max_scale), then the clip
+      const float s_raw = f16_round(g.init * g.mx);
+      const float thr = f16_round(g.thr);
+      bool pass;
+      if (s_raw < 0.f) { s = fminf(s_raw, -thr); pass = (s_raw <= -thr); }
+      else             { s = fmaxf(s_raw, thr);  pass = (s_raw >= thr); }
+      route_mx = pass ? g.init : 0.f;
+      route_mn = 0.f;                                  // min_scale does not enter this graph
+      return;
+    }
     const float lo = -(g.wmin * g.mn);
     const float hi = g.wmax * g.mx;
     const float sgn = (hi < lo) ? 1.f : -1.f;        // "full range": +max maps to -maxq  (int.py:228-230)
@@ -148,7 +160,7 @@ struct MxFp4 {
   bool pass;
 
   __device__ __forceinline__ void setup(const GroupIn& g) {
-    m = g.wmax * g.mx;
+    m = g.wmax * (g.has_init ? g.init * g.mx : g.mx);   // max_val *= init_scale * max_scale (mxfp.py:262-266)
     const float e_raw = (m == 0.f) ? 1.f : log2f(m);
     const float ef = floorf(e_raw) - 2.f;
     e = clampf(ef, -127.f, 127.f);
@@ -174,6 +186,7 @@ struct MxFp4 {
   __device__ __forceinline__ void finish(const GroupAcc& acc, const GroupIn& g, float& dmin, float& dmax) const {
     // s = 2^e, e = floor_ste(log2 m) - 2  =>  ds/dm = s / m ;  m = amax * max_scale
     dmax = pass ? acc.a * (s / m) * g.wmax : 0.f;
+    if (g.has_init) dmax *= g.init;
     dmin = 0.f;
   }
   __device__ __forceinline__ float scale_out() const { return e; }
@@ -200,7 +213,7 @@ struct NvFp4 {
   float route;  // d inv / d max_scale
 
   __device__ __forceinline__ void setup(const GroupIn& g) {
-    const float vmax = g.wmax * g.mx;
+    const float vmax = g.wmax * (g.has_init ? g.mx * g.init : g.mx);   // scale_coeff = max_scale * init_scale (nvfp.py:93-97)
     const float sc_raw = g.gscale * (vmax * 0.16666667163372040f);     // get_reciprocal(6.0) as fp32
     const float sc_c = clampf(sc_raw, -448.f, 448.f);
     sc = e4m3_bits_to_f32(f32_to_e4m3_bits(sc_c));
@@ -211,6 +224,7 @@ struct NvFp4 {
     const bool pass = (sc_raw >= -448.f) && (sc_raw <= 448.f);
     // inv = 1/prod, prod = sc*rg, sc = gs*vmax/6 (STE through e4m3), vmax = amax*mx
     route = (prod != 0.f && pass) ? (-(inv / prod)) * rg * g.gscale * 0.16666667163372040f * g.wmax : 0.f;
+    if (g.has_init) route *= g.init;
   }
   __device__ __forceinline__ float fwd(float w, float v) const {
     const float x = clampf(w * inv + v, -6.f, 6.f);

@@ -62,6 +62,17 @@ def make_spec(name: str, bits: int, group_size: int, n: int, k: int, q_scale_thr
     return Spec(DTYPE_IDS[name], bits, group_size, n, k, q_scale_thresh, scale_bound_hi)
 
 
+def _cspec(spec: "Spec", init_scale=None) -> QSpec:
+    """struct ar_qspec for a call; `init_scale` (fp32 [G], enable_alg_ext) rides in the spec (include/ar_b200.h)."""
+    cs = spec.c()
+    if init_scale is not None:
+        _want(init_scale, torch.float32, "init_scale")
+        if init_scale.numel() != spec.groups:
+            raise ValueError(f"init_scale has {init_scale.numel()} entries, the layer has {spec.groups} groups")
+        cs.init_scale = _p(init_scale)
+    return cs
+
+
 def _p(t):
     if t is None:
         return None
@@ -108,7 +119,7 @@ def scale_dtype_of(spec: Spec):
 
 
 def qdq_fwd(spec: Spec, w, v=None, min_scale=None, max_scale=None, wmin=None, wmax=None, gscale=None,
-            out_wq=None, want_wq=True, want_scale=False):
+            out_wq=None, want_wq=True, want_scale=False, init_scale=None):
     """Fake-quant forward.  Returns (wq bf16 [N,K] | None, scale [G] | None, zp fp32 [G] | None)."""
     _want(w, torch.bfloat16, "w")
     for t, nm in ((v, "v"), (min_scale, "min_scale"), (max_scale, "max_scale"), (gscale, "gscale")):
@@ -116,14 +127,14 @@ def qdq_fwd(spec: Spec, w, v=None, min_scale=None, max_scale=None, wmin=None, wm
     wq = (out_wq if out_wq is not None else torch.empty_like(w)) if want_wq else None
     scale = torch.empty(spec.groups, dtype=scale_dtype_of(spec), device=w.device) if want_scale else None
     zp = torch.empty(spec.groups, dtype=torch.float32, device=w.device) if (want_scale and spec.dtype == DT_INT_ASYM) else None
-    cs = spec.c()
+    cs = _cspec(spec, init_scale)
     _check(_lib.load().ar_qdq_fwd(C.byref(cs), _p(w), _p(v), _p(min_scale), _p(max_scale), _p(wmin), _p(wmax),
                                       _p(gscale), _p(wq), _p(scale), _p(zp), _stream()), "ar_qdq_fwd")
     return wq, scale, zp
 
 
 def qdq_bwd(spec: Spec, w, gq, v=None, min_scale=None, max_scale=None, wmin=None, wmax=None, gscale=None,
-            dv=None, dmin=None, dmax=None, accumulate=False):
+            dv=None, dmin=None, dmax=None, accumulate=False, init_scale=None):
     """Fake-quant backward: Gq fp32 [N,K] -> (dv fp32 [N,Kpad], dmin [G] | None, dmax [G])."""
     _want(w, torch.bfloat16, "w")
     _want(gq, torch.float32, "gq")
@@ -134,7 +145,7 @@ def qdq_bwd(spec: Spec, w, gq, v=None, min_scale=None, max_scale=None, wmin=None
         dmax = torch.empty(spec.groups, dtype=torch.float32, device=dev)
     if dmin is None and spec.is_int:
         dmin = torch.empty(spec.groups, dtype=torch.float32, device=dev)
-    cs = spec.c()
+    cs = _cspec(spec, init_scale)
     _check(_lib.load().ar_qdq_bwd(C.byref(cs), _p(w), _p(v), _p(min_scale), _p(max_scale), _p(wmin), _p(wmax),
                                       _p(gscale), _p(gq), _p(dv), _p(dmin), _p(dmax), int(accumulate), _stream()),
                "ar_qdq_bwd")
@@ -161,11 +172,12 @@ def gemm(a, b, a_mn_major=False, b_mn_major=False, bias=None, out=None):
     return d
 
 
-def fq_linear_fwd(spec: Spec, x2d, w, v, min_scale, max_scale, wmin, wmax, gscale, bias, wq_scratch, out=None):
+def fq_linear_fwd(spec: Spec, x2d, w, v, min_scale, max_scale, wmin, wmax, gscale, bias, wq_scratch, out=None,
+                  init_scale=None):
     _want(x2d, torch.bfloat16, "x")
     t = x2d.shape[0]
     y = out if out is not None else torch.empty(t, spec.n, dtype=torch.bfloat16, device=x2d.device)
-    cs = spec.c()
+    cs = _cspec(spec, init_scale)
     _check(_lib.load().ar_fq_linear_fwd(C.byref(cs), _p(x2d), t, _p(w), _p(v), _p(min_scale), _p(max_scale), _p(wmin),
                                             _p(wmax), _p(gscale), _p(bias), _p(wq_scratch), _p(y), _stream()),
                "ar_fq_linear_fwd")
@@ -182,10 +194,10 @@ def fq_linear_bwd_dx(spec: Spec, dy2d, wq, out=None):
 
 
 def fq_linear_bwd_dw(spec: Spec, dy2d, x2d, w, v, min_scale, max_scale, wmin, wmax, gscale, dv, dmin, dmax,
-                     accumulate=False):
+                     accumulate=False, init_scale=None):
     _want(dy2d, torch.bfloat16, "dy")
     _want(x2d, torch.bfloat16, "x")
-    cs = spec.c()
+    cs = _cspec(spec, init_scale)
     if dv.dtype not in (torch.float32, torch.bfloat16):
         raise TypeError("dv must be fp32 or bf16")
     _check(_lib.load().ar_fq_linear_bwd_dw(C.byref(cs), _p(dy2d), _p(x2d), dy2d.shape[0], _p(w), _p(v), _p(min_scale),
@@ -434,3 +446,34 @@ def imatrix_accum(x2d, imatrix):
         raise ValueError("imatrix_accum: x [rows, K], imatrix [K]")
     _check(_lib.load().ar_imatrix_accum(_p(x2d), x2d.shape[0], x2d.shape[1], _p(imatrix), _stream()), "ar_imatrix_accum")
     return imatrix
+
+
+# ----------------------------------------------------------------------- enable_alg_ext: outlier-suppressed block loss
+class OutlierSelect:
+    """Device scratch of the top-k selection (sign_roundv2/quantizer.py:371-378): the 32768-bin histogram of the bf16
+    pattern of |pred - ref| and sel = [threshold pattern, ties to drop, tie counter]."""
+
+    def __init__(self, device):
+        self.hist = torch.zeros(32768, dtype=torch.int32, device=device)
+        self.sel = torch.zeros(4, dtype=torch.int32, device=device)
+
+
+def mse_outlier_fwd_bwd(pred2d, ref2d, row_mask, upstream, loss_sum, scratch: OutlierSelect, dpred=None, want_grad=True):
+    """SignRoundV2Quantizer._get_loss with its backward: drops the numel // 1000 largest |pred - ref| (selection on the
+    bf16 difference, token mask ignored there), loss_sum (double [1]) += sum((|d| * mask * keep)^2); returns dpred bf16."""
+    _want(pred2d, torch.bfloat16, "pred")
+    _want(ref2d, torch.bfloat16, "ref")
+    _want(loss_sum, torch.float64, "loss_sum")
+    if row_mask is not None:
+        _want(row_mask, torch.uint8, "row_mask")
+    rows, cols = pred2d.shape
+    numel = rows * cols
+    k = max(1, int(numel / 1000))
+    if want_grad and dpred is None:
+        dpred = torch.empty_like(pred2d)
+    lib = _lib.load()
+    _check(lib.ar_absdiff_hist(_p(pred2d), _p(ref2d), numel, _p(scratch.hist), _stream()), "ar_absdiff_hist")
+    _check(lib.ar_topk_threshold(_p(scratch.hist), k, _p(scratch.sel), _stream()), "ar_topk_threshold")
+    _check(lib.ar_mse_outlier_fwd_bwd(_p(pred2d), _p(ref2d), _p(row_mask), rows, cols, float(upstream), _p(scratch.sel),
+                                      _p(loss_sum), _p(dpred if want_grad else None), _stream()), "ar_mse_outlier_fwd_bwd")
+    return dpred

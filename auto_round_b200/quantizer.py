@@ -173,8 +173,11 @@ class SignRoundQuantizer:
                  enable_quanted_input: bool = True, not_use_best_mse: bool = False, amp_dtype=torch.bfloat16,
                  layer_config: Optional[dict] = None, layer_filter=default_layer_filter,
                  dp: Optional[DataParallel] = None, gradient_accumulate_steps: int = 1, use_cuda_graph: bool = True,
-                 fuse_block_ops: bool = True, grad_dtype=None):
+                 fuse_block_ops: bool = True, grad_dtype=None, enable_alg_ext: bool = False):
         self.scheme = scheme
+        # sign_roundv2 (SignRoundV2Quantizer.prepare_run, sign_roundv2/quantizer.py:330-357): symmetric int / mx / nv layers
+        # get a searched init scale with max_scale in [0, 2]; bits < 4 additionally switches to the outlier-suppressed loss
+        self.enable_alg_ext = bool(enable_alg_ext)
         self.iters = iters
         self.lr_is_auto = lr is None
         self.lr = lr
@@ -220,7 +223,21 @@ class SignRoundQuantizer:
         return s
 
     # ---------------------------------------------------------------------------------------------
-    def wrapper_block(self, block: nn.Module, nv_global_scales: Optional[dict] = None):
+    def _optimized(self, sc: QuantizationScheme) -> bool:
+        return self.enable_alg_ext and sc.qdq_name in ("int_sym", "mx_fp4", "nv_fp4")
+
+    def search_init_scale(self, spec, sc: QuantizationScheme, w: torch.Tensor, imatrix):
+        """search_optimized_init_scale (data_type/utils.py:223-254) -> fp32 [G].  The importance vector is broadcast over
+        rows and padded with 1e-5 inside the kernel; unlike the RTN route there is no zero repair here
+        (reshape_imatrix_for_weight, data_type/utils.py:269-282)."""
+        qw = None if imatrix is None else imatrix.reshape(-1).to(torch.float32).contiguous()
+        if sc.qdq_name == "int_sym":
+            return ops.search_scale_int(spec, w, qw, want_wq=False)[0]
+        if sc.qdq_name == "mx_fp4":
+            return ops.search_scale_mx(spec, w, qw)
+        return ops.search_scale_nv(spec, w, qw)
+
+    def wrapper_block(self, block: nn.Module, nv_global_scales: Optional[dict] = None, imatrices: Optional[dict] = None):
         """wrapper.py:774-828: every eligible nn.Linear (bits <= 8) -> WrapperLinear on the block arena."""
         todo = {}
         for name, mod in block.named_modules():
@@ -239,7 +256,10 @@ class SignRoundQuantizer:
         wrapped = {}
         for name, (mod, sc, spec) in todo.items():
             gs = None if nv_global_scales is None else nv_global_scales.get(name)
-            wl = WrapperLinear(mod, sc, spec, arena.layer_views(name), gs)
+            init = None
+            if self._optimized(sc):
+                init = self.search_init_scale(spec, sc, mod.weight.data.contiguous(), (imatrices or {}).get(name))
+            wl = WrapperLinear(mod, sc, spec, arena.layer_views(name), gs, init)
             set_module(block, name, wl)
             wrapped[name] = wl
         return wrapped, arena
@@ -320,7 +340,7 @@ class SignRoundQuantizer:
                 token_masks = torch.stack(masks).to(device=device, dtype=torch.uint8).contiguous()
         valid_per_sample = None if token_masks is None else token_masks.sum(dim=1).cpu().tolist()
 
-        wrapped, arena = self.wrapper_block(block, nv_global_scales)
+        wrapped, arena = self.wrapper_block(block, nv_global_scales, kwargs.get("imatrices"))
         self.last_arena = arena if kwargs.get("keep_arena") else None
         res = TuneResult(quantized_layers=list(wrapped))
         self.last_result = res
@@ -372,6 +392,19 @@ class SignRoundQuantizer:
         from .moe import LinearLoopExperts
         has_moe = any(isinstance(m, LinearLoopExperts) for m in block.modules())   # ragged, data-dependent shapes
 
+        # enable_alg_ext loss (SignRoundV2Quantizer._get_loss, sign_roundv2/quantizer.py:362-399): bits < 4 -> the numel/1000
+        # largest |pred - ref| are dropped; otherwise it falls back to the base MSE WITHOUT forwarding the valid-token mask
+        optimized = [wl for wl in wrapped.values() if wl.init_scale is not None]
+        outlier_loss = bool(optimized) and self.scheme.sym and self.scheme.bits < 4
+        unmasked_loss = bool(optimized) and not outlier_loss
+        clamp_hi = 2.0 if optimized else 1.0                        # minmax_scale_bound (sign_roundv2/quantizer.py:102)
+        if optimized and len(optimized) != len(wrapped):
+            raise NotImplementedError("enable_alg_ext with mixed optimized / plain layers in one block (per-layer bounds)")
+        if outlier_loss and dp.world > 1:
+            raise NotImplementedError("enable_alg_ext outlier-suppressed loss under data parallelism: the top-k is global over "
+                                      "the batch; a cross-rank histogram reduce is not built")
+        outlier_scratch = ops.OutlierSelect(device) if outlier_loss else None
+
         def fwd_bwd():
             ops.sched_load(idx_dev, inv_tab, it_dev, lbs, cur32, cur64, cur_inv)
             ops.gather_rows(x_all, cur32, out=x_buf)
@@ -388,16 +421,20 @@ class SignRoundQuantizer:
             pred2d = pred.reshape(-1, hidden)
             if pred2d.dtype != torch.bfloat16:
                 pred2d = pred2d.to(torch.bfloat16)
-            dpred = ops.mse_fwd_bwd(pred2d.contiguous(), ref_buf.reshape(-1, hidden), mask_rows, inv_numel, 1000.0,
-                                    loss_sum)
+            if outlier_loss:
+                dpred = ops.mse_outlier_fwd_bwd(pred2d.contiguous(), ref_buf.reshape(-1, hidden), mask_rows, 1000.0, loss_sum,
+                                                outlier_scratch)
+            else:
+                dpred = ops.mse_fwd_bwd(pred2d.contiguous(), ref_buf.reshape(-1, hidden), None if unmasked_loss else mask_rows,
+                                        inv_numel, 1000.0, loss_sum)
             pred.backward(dpred.view_as(pred).to(pred.dtype))
 
         def update(last: bool):
             ops.best_update(loss_sum, inv_numel, 1.0, 0, state, flag, hist, inv_num_elm_dev=cur_inv, it_dev=it_dev)
             if self.not_use_best_mse:
                 flag.fill_(1 if last else 0)
-            ops.signsgd_step(arena.params, arena.grads_v, arena.best, flag, lr_tab, 0, arena.clamp_begin, 1.0, it_dev=it_dev,
-                             g_scales=arena.grads_s)
+            ops.signsgd_step(arena.params, arena.grads_v, arena.best, flag, lr_tab, 0, arena.clamp_begin, clamp_hi,
+                             it_dev=it_dev, g_scales=arena.grads_s)
             ops.iter_advance(it_dev)
 
         def eager_iteration(it):

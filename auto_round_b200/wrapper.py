@@ -35,7 +35,7 @@ class _FQLinearFn(torch.autograd.Function):
         x2d = x2d.contiguous()
         y = ops.fq_linear_fwd(layer.spec, x2d, layer.weight, layer.value, layer.min_scale, layer.max_scale,
                               layer.weight_min, layer.weight_max, layer.weight_global_scale, layer.bias_bf16,
-                              layer.wq)
+                              layer.wq, init_scale=layer.init_scale)
         ctx.layer = layer
         ctx.x_dtype = x.dtype
         ctx.save_for_backward(x2d)
@@ -51,7 +51,8 @@ class _FQLinearFn(torch.autograd.Function):
         dy2d = dy2d.contiguous()
         ops.fq_linear_bwd_dw(layer.spec, dy2d, x2d, layer.weight, layer.value, layer.min_scale, layer.max_scale,
                              layer.weight_min, layer.weight_max, layer.weight_global_scale, layer.grad_value,
-                             layer.grad_min_scale, layer.grad_max_scale, accumulate=layer.grad_accumulate)
+                             layer.grad_min_scale, layer.grad_max_scale, accumulate=layer.grad_accumulate,
+                             init_scale=layer.init_scale)
         layer.grad_accumulate = True           # further micro-batches of this iteration add up
         dx = None
         if ctx.needs_input_grad[0]:
@@ -66,8 +67,11 @@ class WrapperLinear(nn.Module):
     slices of the block arena handed in by the quantizer."""
 
     def __init__(self, orig_layer: nn.Linear, scheme: QuantizationScheme, spec: ops.Spec, arena_views: dict,
-                 global_scale=None):
+                 global_scale=None, init_scale=None):
         super().__init__()
+        # enable_alg_ext (SignRoundOptimizedWrapperLinear, sign_roundv2/quantizer.py:101-125): searched per-group initial
+        # scale, fp32 [G]; the tunable max_scale (bound [0, 2]) multiplies it and min_scale is inert
+        self.init_scale = init_scale
         self.orig_layer = orig_layer
         self.scheme = scheme
         self.spec = spec
@@ -109,7 +113,7 @@ class WrapperLinear(nn.Module):
         # best == {} -> plain RTN (iters == 0): V = 0, scales = 1, range math in the weight dtype like the reference
         wq, scale, zp = ops.qdq_fwd(spec, self.weight, best.get("value"), best.get("min_scale"), best.get("max_scale"),
                                     self.weight_min, self.weight_max, self.weight_global_scale, out_wq=self.wq,
-                                    want_scale=True)
+                                    want_scale=True, init_scale=self.init_scale)
         lin = self.orig_layer
         lin.weight.data.copy_(wq)
         n = spec.n

@@ -59,6 +59,10 @@ typedef struct ar_qspec {
   int32_t k;              /* cols of W (in features) */
   float q_scale_thresh;   /* 1e-5 (fp16 scale) / 1e-8 (fp32 scale): auto_round/wrapper.py:115-118 */
   float scale_bound_hi;   /* upper clamp of min/max_scale: 1.0 (wrapper.py:76) or 2.0 (alg_ext) */
+  const float* init_scale; /* NULL, or DEVICE fp32 [N*ceil(K/g)]: enable_alg_ext's searched per-group initial scale
+                              (sign_roundv2/quantizer.py:101-125).  int_sym: scale = fp16(init_scale * max_scale), min_scale
+                              unused (int.py:201-216); mx/nv: the group amax is multiplied by init_scale * max_scale
+                              (mxfp.py:262-266, nvfp.py:93-97).  Honoured by ar_qdq_fwd/_bwd and ar_fq_linear_*. */
 } ar_qspec;
 
 /* Per-group min/max of W clamped at 0 (bf16 out, [G]) -- auto_round/wrapper.py:154-167. */
@@ -246,6 +250,19 @@ int ar_search_scale_nv(const void* w_bf16, const float* qw, long long qw_row_str
                        const float* coef, int ncand, const ar_qspec* spec, float* coeff_out, void* stream);
 int ar_search_scale_mx(const void* w_bf16, const float* qw, long long qw_row_stride, const float* coef, int ncand,
                        const ar_qspec* spec, float* coeff_out, void* stream);
+/*
+ * Outlier-suppressed block loss of enable_alg_ext -- replaces SignRoundV2Quantizer._get_loss
+ * (auto_round/algorithms/quantization/sign_roundv2/quantizer.py:362-399; torch.topk over numel elements per iteration).
+ *   ar_absdiff_hist:   hist[32768] (u32, zero before the first call) += histogram of the bf16 bit pattern of |pred - ref|
+ *   ar_topk_threshold: from the histogram and k = max(1, numel / 1000): sel[0] = threshold pattern, sel[1] = how many elements
+ *                      AT the threshold are dropped, sel[2] = 0 (tie counter); re-zeroes hist
+ *   ar_mse_outlier_fwd_bwd: loss_sum (double, unnormalised) += sum((|pred-ref| * row_mask * keep)^2); dpred (bf16, nullable)
+ *                      = d(upstream * mean(...)) / d pred.  keep drops patterns > sel[0] and the first sel[1] found at sel[0].
+ */
+int ar_absdiff_hist(const void* pred_bf16, const void* ref_bf16, int64_t numel, uint32_t* hist, void* stream);
+int ar_topk_threshold(uint32_t* hist, int64_t k, uint32_t* sel, void* stream);
+int ar_mse_outlier_fwd_bwd(const void* pred_bf16, const void* ref_bf16, const uint8_t* row_mask, int64_t rows, int64_t cols,
+                           float upstream, uint32_t* sel, double* loss_sum, void* dpred_bf16, void* stream);
 /* importance matrix: imatrix[k] += sum over rows of x[row,k]^2 (algorithms/quantization/rtn/quantizer.py:86-105) */
 int ar_imatrix_accum(const void* x_bf16, long long rows, int k, float* imatrix, void* stream);
 
