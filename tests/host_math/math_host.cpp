@@ -1,0 +1,57 @@
+// TEST INFRASTRUCTURE: the product's device math header (auto_round_b200/csrc/ar_qdq_math.cuh) compiled as plain host C++
+// (g++, no nvcc, no GPU) behind a C entry point, so that the fake-quant forward/backward formulas -- including the
+// enable_alg_ext init_scale branches that have not run on hardware yet -- can be checked against the oracle in the CPU
+// test tier.  The CUDA headers provide host versions of the fp16 / bf16 / e4m3 conversions; the only shim is
+// __uint_as_float.  Group handling mirrors qdq_fwd_kernel / qdq_bwd_kernel (ar_qdq.cu): wmin/wmax clamped at 0, fp4 amax,
+// sequential (not shuffle-tree) group sums.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+#include "../../auto_round_b200/csrc/ar_qdq_math.cuh"
+
+namespace {
+template <class Ctx, bool FP4>
+void run(int bits, int g, long groups, const float* w, const float* v, const float* mn, const float* mx, const float* init,
+         float gscale, float thr, const float* gq, float* wq, float* scale, float* zp, float* dv, float* dmin, float* dmax) {
+  for (long gi_ = 0; gi_ < groups; ++gi_) {
+    const float* wg = w + gi_ * g;
+    ar::GroupIn gi;
+    gi.thr = thr; gi.gscale = gscale; gi.plain = (mn == nullptr) && (mx == nullptr);
+    gi.mn = mn ? mn[gi_] : 1.f; gi.mx = mx ? mx[gi_] : 1.f;
+    gi.has_init = (init != nullptr); gi.init = init ? init[gi_] : 1.f;
+    if (FP4) {
+      float m = 0.f;
+      for (int i = 0; i < g; ++i) m = fmaxf(m, fabsf(wg[i]));
+      gi.wmax = m; gi.wmin = 0.f;
+    } else {
+      float lo = 0.f, hi = 0.f;
+      for (int i = 0; i < g; ++i) { lo = fminf(lo, wg[i]); hi = fmaxf(hi, wg[i]); }
+      gi.wmin = lo; gi.wmax = hi;
+    }
+    Ctx ctx; ctx.init(bits); ctx.setup(gi);
+    ar::GroupAcc acc;
+    for (int i = 0; i < g; ++i) {
+      const float vv = v ? v[gi_ * g + i] : 0.f;
+      if (wq) wq[gi_ * g + i] = ar::bf16_round(ctx.fwd(wg[i], vv));
+      if (gq) { float d; ctx.bwd(wg[i], vv, gq[gi_ * g + i], d, acc); dv[gi_ * g + i] = d; }
+    }
+    if (scale) scale[gi_] = ctx.scale_out();
+    if (zp) zp[gi_] = ctx.zp_out();
+    if (gq) { float a, b; ctx.finish(acc, gi, a, b); if (dmin) dmin[gi_] = a; if (dmax) dmax[gi_] = b; }
+  }
+}
+}  // namespace
+
+// dtype: 0 int_sym, 1 int_asym, 2 mx_fp4, 3 nv_fp4 (AR_DT_*).  w holds bf16 values as fp32.  Any output may be NULL.
+extern "C" int host_qdq(int dtype, int bits, int g, long groups, const float* w, const float* v, const float* mn, const float* mx,
+                        const float* init, float gscale, float thr, const float* gq, float* wq, float* scale, float* zp,
+                        float* dv, float* dmin, float* dmax) {
+  switch (dtype) {
+    case 0: run<ar::IntSym, false>(bits, g, groups, w, v, mn, mx, init, gscale, thr, gq, wq, scale, zp, dv, dmin, dmax); return 0;
+    case 1: run<ar::IntAsym, false>(bits, g, groups, w, v, mn, mx, init, gscale, thr, gq, wq, scale, zp, dv, dmin, dmax); return 0;
+    case 2: run<ar::MxFp4, true>(bits, g, groups, w, v, mn, mx, init, gscale, thr, gq, wq, scale, zp, dv, dmin, dmax); return 0;
+    case 3: run<ar::NvFp4, true>(bits, g, groups, w, v, mn, mx, init, gscale, thr, gq, wq, scale, zp, dv, dmin, dmax); return 0;
+  }
+  return -1;
+}
