@@ -123,3 +123,45 @@ def test_device_math_on_host_matches_oracle(host_math, name, dt, qname, bits, g,
         else:
             ref_dn = mnp.grad
             assert float((got["dmin"] - ref_dn).abs().max() / ref_dn.abs().max().clamp_min(1e-12)) <= tol, name
+
+
+def _bits_of_absdiff(pred, ref):
+    """bf16 bit pattern (15 bits) of |pred - ref| as `torch.abs(pred - ref)` holds it -- absdiff_bits() in ar_outlier.cu."""
+    return (torch.abs(pred - ref).view(torch.int16).to(torch.int32) & 0x7FFF).reshape(-1)
+
+
+@pytest.mark.parametrize("rows,cols,seed", [(64, 64, 0), (512, 1024, 1), (37, 8, 2)])
+def test_histogram_threshold_selects_the_topk_set(rows, cols, seed):
+    """The algorithm of ar_outlier.cu restated with numpy-level ops (histogram of the bf16 pattern -> suffix scan ->
+    threshold + tie budget), against torch.topk as the reference's _get_loss uses it: same number of dropped elements, same
+    set above the threshold, and -- because elements AT the threshold have the same |bf16 diff| -- the same bf16-level loss
+    up to which tie members are dropped."""
+    gen = torch.Generator().manual_seed(seed)
+    ref = torch.randn(rows, cols, generator=gen).bfloat16()
+    pred = (ref.float() + 0.05 * torch.randn(rows, cols, generator=gen)).bfloat16()
+    numel = rows * cols
+    k = max(1, int(numel / 1000))
+    bits = _bits_of_absdiff(pred, ref)
+    hist = torch.bincount(bits, minlength=32768)
+    suffix = torch.flip(torch.cumsum(torch.flip(hist, [0]), 0), [0])          # suffix[t] = count(pattern >= t)
+    thr = int(torch.nonzero(suffix >= k).max())                                # largest t with count(>= t) >= k
+    above = int(suffix[thr + 1]) if thr + 1 < 32768 else 0
+    need = k - above
+    assert above < k <= above + int(hist[thr]) and 1 <= need <= int(hist[thr])
+    # torch.topk's choice
+    _, top = torch.topk(torch.abs(pred - ref).view(-1).abs(), k)
+    dropped = torch.zeros(numel, dtype=torch.bool)
+    dropped[top] = True
+    assert bool(dropped[bits > thr].all())                                    # everything above the threshold is dropped
+    assert not bool(dropped[bits < thr].any())                                # nothing below it
+    assert int(dropped[bits == thr].sum()) == need                            # and exactly `need` of the ties
+    # loss: dropping ANY `need` tie members changes the sum only through the fp32 |diff| of members with equal bf16 |diff|
+    d = (pred.float() - ref.float()).abs().reshape(-1)
+    mine = dropped.clone()
+    mine[bits == thr] = False
+    tie_idx = torch.nonzero(bits == thr).reshape(-1)[:need]                    # first-come choice, as the kernel's counter
+    mine[tie_idx] = True
+    l_ref = float(((d * (~dropped)) ** 2).mean())
+    l_mine = float(((d * (~mine)) ** 2).mean())
+    assert l_mine == pytest.approx(l_ref, rel=1e-3)
+    assert l_mine == pytest.approx(float(S.outlier_suppressed_loss(pred, ref, None)), rel=1e-3)
