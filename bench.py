@@ -333,8 +333,14 @@ def cpu_baseline(budget_s: float = 25.0, threads=None):
 
     from oracle import signround as S
 
-    if threads:
-        torch.set_num_threads(threads)
+    if threads is None:
+        # all the host cores this process may use -- torchrun exports OMP_NUM_THREADS=1 to every rank, which would
+        # otherwise turn the reference arm into a single-threaded run at N > 1
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    torch.set_num_threads(max(1, int(threads)))
     cores = torch.get_num_threads()
     cfg = LlamaConfig(num_hidden_layers=1, **LLAMA3_8B)
     cfg._attn_implementation = "sdpa"
