@@ -12,6 +12,7 @@ AutoScheme, MLLM / diffusion calibration, torch.compile, CPU execution.
 """
 from __future__ import annotations
 
+import json
 import os
 import random
 import time
@@ -22,6 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import export, ops
+from . import resume as resume_mod
 from .fused import fused_block_ops
 from .moe import unfuse_experts
 from .quantizer import DataParallel, SignRoundQuantizer
@@ -442,7 +444,26 @@ class AutoRound:
         t0 = time.time()                                                  # orchestrator.py:631
         q_inputs = None
         nblk = len(blocks)
+        # AR_RESUME_DIR (utils/resume.py, orchestrator.py:634-676): skip the blocks a previous process finished, restore
+        # their results and the two chain values, and persist the same after every block of this run
+        resume, start = self._open_resume(prefix, blocks)
+        if resume is not None and start > 0:
+            fp_chain, q_chain, rng = resume.load_input_ids(), resume.load_q_input(), None
+            if fp_chain is None:
+                raise RuntimeError(f"AR_RESUME_DIR: manifest lists {start} finished blocks but the chained inputs are missing")
+            for bj in range(start):
+                snap = resume.load_block(f"{prefix}.{bj}")
+                rng = snap.pop("__rng__", rng)
+                resume_mod.restore_block(blocks[bj], snap, quantizer.scheme_for)
+                self.block_results.append({"block": f"{prefix}.{bj}", "resumed": True})
+            fp_inputs = [t.to(self.device) for t in fp_chain]
+            q_inputs = None if q_chain is None else [t.to(self.device) for t in q_chain]
+            if rng is not None:                                           # the sampler continues where the dead run was
+                random.setstate(rng["python"])
+                torch.set_rng_state(rng["torch"])
         for bi, block in enumerate(blocks):
+            if bi < start:
+                continue
             tb = time.time()
             self._hook(bi, "h2d0")
             block.to(self.device)                                         # H2D of this block's weights
@@ -487,11 +508,17 @@ class AutoRound:
             block.to("cpu")                                               # packed tensors (or qdq weights) -> host
             self._hook(bi, "done")
             torch.cuda.synchronize(self.device)
+            if resume is not None and self.dp.rank == 0:                  # one writer; every rank holds identical results
+                snap = resume_mod.snapshot_block(block)
+                snap["__rng__"] = {"python": random.getstate(), "torch": torch.get_rng_state()}
+                resume.mark_block_done(f"{prefix}.{bi}", snap, q_inputs, fp_inputs)
             phases = {k: ev[i].elapsed_time(ev[i + 1]) for i, k in enumerate(("ref_forward_ms", "tune_ms", "q_forward_ms", "pack_ms"))}
             self.block_results.append({"block": f"{prefix}.{bi}", "init_loss": res.init_loss, "best_loss": res.best_loss,
                                        "best_iter": res.best_iter, "seconds": time.time() - tb, "losses": res.losses,
                                        "phases_ms": phases, "cuda_graph": res.used_cuda_graph})
         self.timings["tuning_s"] = time.time() - t0                      # "quantization tuning time" (orchestrator.py:792)
+        if resume is not None and self.dp.rank == 0:
+            resume.clear()                                                # a finished run leaves no state behind
         self.quantized = True
         self._packed = self._pack_on_the_fly
         self.block_prefix = prefix
@@ -502,6 +529,22 @@ class AutoRound:
                     layer_cfg[f"{prefix}.{bi}.{n}"] = self.scheme.to_dict()
         self.layer_config_out = layer_cfg
         return model, layer_cfg
+
+    def _open_resume(self, prefix: str, blocks):
+        """-> (ResumeState | None, index of the first block still to do).  Active only when AR_RESUME_DIR is set."""
+        rd = os.environ.get("AR_RESUME_DIR")
+        if not rd:
+            return None, 0
+        names = [f"{prefix}.{i}" for i in range(len(blocks))]
+        model_id = getattr(getattr(self.model, "config", None), "_name_or_path", None)
+        scheme_desc = (json.dumps(self.scheme.to_dict(), sort_keys=True, default=str) + "|"
+                       + resume_mod.layer_config_fingerprint(self.layer_config)
+                       + f"|iters={self.iters}|bs={self.batch_size}|seed={self.seed}|alg_ext={getattr(self, 'enable_alg_ext', False)}"
+                       + f"|pack={self._pack_on_the_fly}|{sorted(self.sign_kw.items())}")
+        sig = resume_mod.compute_run_signature(model_id, scheme_desc, resume_mod.dataset_fingerprint(self.dataset), self.nsamples,
+                                               self.seqlen, names)
+        st = resume_mod.ResumeState(os.path.join(rd, "group_0"), sig, names)
+        return st, st.resume_index
 
     def _rtn_mode(self) -> str:
         """Which RTN the reference runs for iters == 0 (`_select_rtn_compressor_base_cls`, autoround.py:250-318, and

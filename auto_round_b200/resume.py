@@ -1,0 +1,234 @@
+"""Crash-resume of the block-sequential tuning run -- host-side mirror of auto_round/utils/resume.py.
+
+Activated exactly like the reference: set `AR_RESUME_DIR`.  After every block the run persists
+  * the block's RESULT (packed `QuantLinear` buffers, or the qdq weight + scale / zp / global scale of each tuned linear),
+  * the two chain values the next block needs verbatim -- the full-precision block outputs (next block's reference input)
+    and, with `enable_quanted_input`, the quantised block's outputs (utils/resume.py:8-22 explains why both must be the live
+    values, not recomputed ones),
+  * a manifest `{signature, completed_blocks}` written atomically (tmp file + os.replace), trusted only when the signature
+    (model id, scheme + per-layer config, dataset, nsamples, seqlen, block list) matches and `completed_blocks` is a PREFIX
+    of the current block order (utils/resume.py:96-119).
+The reference keeps finished blocks in its ShardWriter / offloader directories; this engine has neither, so the per-block
+result files live in the resume directory itself.
+
+Everything here is plain torch / json on host tensors: no CUDA, covered by tests/test_resume.py in the CPU tier.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import tempfile
+from pathlib import Path
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+MANIFEST = "resume_manifest.json"
+Q_INPUT = "resume_q_input.pt"
+FP_INPUT = "resume_input_ids.pt"      # the reference's name for the chained full-precision hidden states
+
+_SCALARS = (int, float, bool, str, type(None))
+
+
+def _to_cpu(obj):
+    if isinstance(obj, torch.Tensor):
+        return obj.detach().to("cpu")
+    if isinstance(obj, dict):
+        return {k: _to_cpu(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_to_cpu(v) for v in obj)
+    return obj
+
+
+def _atomic_write_json(path: Path, data: dict) -> None:
+    fd, tmp = tempfile.mkstemp(dir=str(path.parent), prefix=".tmp_resume_")
+    try:
+        with os.fdopen(fd, "w") as f:
+            json.dump(data, f)
+        os.replace(tmp, path)
+    except Exception:
+        try:
+            os.remove(tmp)
+        except OSError:
+            pass
+        raise
+
+
+def _atomic_save(obj, path: Path) -> None:
+    fd, tmp = tempfile.mkstemp(dir=str(path.parent), prefix=".tmp_resume_")
+    try:
+        with os.fdopen(fd, "wb") as f:                 # a file object: torch.save derives archive names from paths otherwise
+            torch.save(obj, f)
+        os.replace(tmp, path)
+    except Exception:
+        try:
+            os.remove(tmp)
+        except OSError:
+            pass
+        raise
+
+
+def layer_config_fingerprint(layer_config) -> str:
+    """utils/resume.py:185-222: scalar per-layer settings only, deterministic order."""
+    if not layer_config:
+        return "<no-layer-config>"
+    parts = []
+    for name in sorted(layer_config):
+        cfg = layer_config[name]
+        if hasattr(cfg, "to_dict"):
+            cfg = cfg.to_dict()
+        if isinstance(cfg, dict):
+            desc = ",".join(f"{k}={v}" for k, v in sorted(cfg.items(), key=lambda kv: str(kv[0])) if isinstance(v, _SCALARS))
+        else:
+            desc = str(cfg)
+        parts.append(f"{name}:{desc}")
+    return ";".join(parts)
+
+
+def compute_run_signature(model_id: Optional[str], scheme_desc: str, dataset_desc: str, nsamples: int, seqlen: int,
+                          block_names: list) -> str:
+    """utils/resume.py:166-182."""
+    h = hashlib.sha256()
+    for part in (model_id or "", scheme_desc, dataset_desc, str(nsamples), str(seqlen), "|".join(block_names)):
+        h.update(part.encode("utf-8"))
+        h.update(b"\x00")
+    return h.hexdigest()
+
+
+def dataset_fingerprint(dataset) -> str:
+    """Token-tensor datasets have no stable `str()`: hash their contents instead."""
+    if dataset is None or isinstance(dataset, str):
+        return str(dataset)
+    h = hashlib.sha256()
+    for t in dataset:
+        t = torch.as_tensor(t).detach().to("cpu", torch.int64).contiguous()
+        h.update(str(tuple(t.shape)).encode())
+        h.update(t.numpy().tobytes())
+    return "tokens:" + h.hexdigest()
+
+
+# ------------------------------------------------------------------------------------------ per-block result snapshot
+_LAYER_ATTRS = ("scale", "zp", "weight_global_scale")
+
+
+def snapshot_block(block: nn.Module) -> dict:
+    """Host copy of what tuning changed in `block`: for packed layers every buffer of the QuantLinear holder (plus the
+    constructor facts), for unpacked ones the qdq weight and the scale / zp / global-scale attributes."""
+    from .export import QuantLinear
+
+    out = {}
+    for name, m in block.named_modules():
+        if isinstance(m, QuantLinear):
+            out[name] = {"kind": "packed", "in_features": m.in_features, "out_features": m.out_features,
+                         "buffers": {k: v.detach().cpu() for k, v in m._buffers.items() if v is not None},
+                         "non_persistent": sorted(m._non_persistent_buffers_set)}
+        elif isinstance(m, nn.Linear) and hasattr(m, "scale"):
+            rec = {"kind": "qdq", "weight": m.weight.detach().cpu()}
+            for a in _LAYER_ATTRS:
+                if hasattr(m, a):
+                    rec[a] = _to_cpu(getattr(m, a))
+            out[name] = rec
+    return out
+
+
+def restore_block(block: nn.Module, snap: dict, scheme_for) -> list:
+    """Inverse of snapshot_block on a freshly loaded (unquantised) `block`.  `scheme_for(name, module)` supplies the
+    QuantizationScheme a packed holder is labelled with.  Returns the restored layer names."""
+    from .export import QuantLinear
+    from .wrapper import set_module
+
+    done = []
+    for name, rec in snap.items():
+        lin = block.get_submodule(name)
+        if rec["kind"] == "packed":
+            bias = rec["buffers"].get("bias")
+            bufs = {k: v for k, v in rec["buffers"].items() if k != "bias"}
+            set_module(block, name, QuantLinear(rec["in_features"], rec["out_features"], scheme_for(name, lin), bufs, bias))
+        else:
+            lin.weight.data = rec["weight"].to(lin.weight.dtype)
+            for a in _LAYER_ATTRS:
+                if a in rec:
+                    setattr(lin, a, rec[a])
+        done.append(name)
+    return done
+
+
+class ResumeState:
+    """utils/resume.py:74-164 plus the per-block result files described in the module docstring."""
+
+    def __init__(self, resume_dir: str, signature: str, block_names: list):
+        self.dir = Path(resume_dir)
+        self.dir.mkdir(parents=True, exist_ok=True)
+        self.signature = signature
+        self.block_names = list(block_names)
+        self.manifest_path = self.dir / MANIFEST
+        self.completed_blocks: list = []
+        self._load()
+
+    def _block_path(self, name: str) -> Path:
+        return self.dir / ("block_" + name.replace("/", "_") + ".pt")
+
+    def _load(self) -> None:
+        if not self.manifest_path.exists():
+            return
+        try:
+            with open(self.manifest_path) as f:
+                data = json.load(f)
+        except Exception:  # noqa: BLE001 -- a corrupt manifest means "start fresh", like the reference
+            return
+        if data.get("signature") != self.signature:
+            return
+        completed = data.get("completed_blocks", [])
+        if completed != self.block_names[: len(completed)]:
+            return
+        if not all(self._block_path(n).exists() for n in completed):
+            return                                   # a result file is missing: the manifest overstates what is durable
+        self.completed_blocks = list(completed)
+
+    @property
+    def resume_index(self) -> int:
+        return len(self.completed_blocks)
+
+    def _load_tensor(self, name: str):
+        p = self.dir / name
+        if not self.completed_blocks or not p.exists():
+            return None
+        try:
+            return torch.load(p, map_location="cpu", weights_only=False)
+        except Exception:  # noqa: BLE001
+            return None
+
+    def load_q_input(self):
+        return self._load_tensor(Q_INPUT)
+
+    def load_input_ids(self):
+        return self._load_tensor(FP_INPUT)
+
+    def load_block(self, name: str) -> dict:
+        return torch.load(self._block_path(name), map_location="cpu", weights_only=False)
+
+    def mark_block_done(self, block_name: str, block_snapshot: dict, q_input, fp_input) -> None:
+        expected = self.block_names[len(self.completed_blocks)]
+        if block_name != expected:
+            raise AssertionError(f"ResumeState.mark_block_done out of order: expected {expected!r}, got {block_name!r}")
+        _atomic_save(block_snapshot, self._block_path(block_name))
+        qp = self.dir / Q_INPUT
+        if q_input is not None:
+            _atomic_save(_to_cpu(q_input), qp)
+        elif qp.exists():
+            qp.unlink()
+        _atomic_save(_to_cpu(fp_input), self.dir / FP_INPUT)       # required: the FP reference chain always exists
+        self.completed_blocks.append(block_name)
+        # the manifest is written LAST: a crash before this line re-does the block instead of skipping it
+        _atomic_write_json(self.manifest_path, {"signature": self.signature, "completed_blocks": self.completed_blocks})
+
+    def clear(self) -> None:
+        for p in [self.manifest_path, self.dir / Q_INPUT, self.dir / FP_INPUT] + [self._block_path(n) for n in self.block_names]:
+            if p.exists():
+                try:
+                    p.unlink()
+                except OSError:
+                    pass
+        self.completed_blocks = []
