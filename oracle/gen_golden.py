@@ -379,3 +379,79 @@ if __name__ == "__main__" and "rtn" in sys.argv[1:]:
     gen_rtn_export("opt_w4a16_sym_g32", dict(scheme="W4A16", group_size=32), opt=True)
     gen_rtn_export("opt_nvfp4", dict(scheme="NVFP4", act_bits=16, act_data_type="float"), opt=True)
     gen_rtn_export("opt_mxfp4", dict(scheme="MXFP4", act_bits=16), opt=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# lm_head fixture: `quant_lm_head=True` sends the output projection through
+# SignRoundQuantizer.quantize_layer_outside_block (sign_round/quantizer.py:554-759): micro-batches of one sample,
+# gradients accumulated over `batch_size` samples per iteration, MSELoss(reduction="sum"), num_elm fixed before the loop.
+# ---------------------------------------------------------------------------------------------
+def gen_lm_head(tag, scheme_kwargs, iters=8, nsamples=8, seqlen=16, batch_size=4):
+    import auto_round.algorithms.quantization.sign_round.quantizer as qz
+    import auto_round.compressors.utils as cu
+    from auto_round import AutoRound
+    from oracle.ref_shim import DummyTokenizer
+
+    model = tiny_llama()
+    init_state = {k: v.clone() for k, v in model.state_dict().items()}
+    tokens = torch.randint(0, 128, (nsamples, seqlen), generator=torch.Generator().manual_seed(1))
+    dataset = [tokens[i:i + batch_size] for i in range(0, nsamples, batch_size)]
+    rec = {"tokens": tokens, "init_state": init_state, "iters": iters, "batch_size": batch_size, "scheme_kwargs": scheme_kwargs,
+           "layers": []}
+    cur = {"active": False}
+    orig_ql = qz.SignRoundQuantizer.quantize_layer_outside_block
+    orig_next = cu.IndexSampler.next_batch
+    orig_bwd = qz.SignRoundQuantizer._scale_loss_and_backward
+
+    def clone_list(x):
+        return None if x is None else [t.detach().clone() for t in x]
+
+    def ql(self, layer, fp_inputs=None, q_inputs=None, disable_opt_rtn=None, input_ids=None):
+        cur.update(active=True, name=layer.global_name, fp_inputs=clone_list(fp_inputs), q_inputs=clone_list(q_inputs),
+                   input_ids=clone_list(input_ids), weight=layer.weight.detach().clone(),
+                   bias=None if layer.bias is None else layer.bias.detach().clone(), batches=[], losses=[])
+        r = orig_ql(self, layer, fp_inputs=fp_inputs, q_inputs=q_inputs, disable_opt_rtn=disable_opt_rtn, input_ids=input_ids)
+        from auto_round.utils import get_module
+        m = get_module(self.model, cur["name"])
+        out = {k: v for k, v in cur.items() if k != "active"}
+        out.update(out_weight=m.weight.detach().clone(), scale=m.scale.detach().clone() if hasattr(m, "scale") else None,
+                   zp=m.zp.detach().clone() if isinstance(getattr(m, "zp", None), torch.Tensor) else getattr(m, "zp", None))
+        rec["layers"].append(out)
+        cur["active"] = False
+        return r
+
+    def nb(self):
+        b = orig_next(self)
+        if cur["active"]:
+            cur["batches"].append(list(b))
+        return b
+
+    def bwd(self, scaler, loss):
+        if cur["active"]:
+            cur["losses"].append(float(loss.item()))
+        return orig_bwd(self, scaler, loss)
+
+    qz.SignRoundQuantizer.quantize_layer_outside_block = ql
+    cu.IndexSampler.next_batch = nb
+    qz.SignRoundQuantizer._scale_loss_and_backward = bwd
+    try:
+        ar = AutoRound(model, tokenizer=DummyTokenizer(), iters=iters, nsamples=nsamples, seqlen=seqlen, batch_size=batch_size,
+                       dataset=dataset, device_map="cpu", enable_torch_compile=False, seed=42, quant_lm_head=True,
+                       **scheme_kwargs)
+        ar.quantize()
+    finally:
+        qz.SignRoundQuantizer.quantize_layer_outside_block = orig_ql
+        cu.IndexSampler.next_batch = orig_next
+        qz.SignRoundQuantizer._scale_loss_and_backward = orig_bwd
+    torch.save(rec, os.path.join(GOLDEN, f"lm_head_{tag}.pt"))
+    for lay in rec["layers"]:
+        print(f"lm_head_{tag}.pt:", lay["name"], "fp_inputs", None if lay["fp_inputs"] is None else len(lay["fp_inputs"]),
+              "q_inputs", None if lay["q_inputs"] is None else len(lay["q_inputs"]), "losses", lay["losses"][:3],
+              "batches", lay["batches"][:2])
+
+
+if __name__ == "__main__" and "lm_head" in sys.argv[1:]:
+    from oracle.ref_shim import import_reference as _imp2
+
+    _imp2()
+    gen_lm_head("w4a16_sym_g32", dict(scheme="W4A16", group_size=32))

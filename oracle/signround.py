@@ -345,3 +345,93 @@ def tune_block(block, inputs, others, fp_outputs, scheme_of, iters=200, batch_si
     with torch.no_grad():
         unwrap_block(block, wrapped, res.best_params)
     return res
+
+
+# --------------------------------------------------------------------------------------------
+# quantize_layer_outside_block -- auto_round/algorithms/quantization/sign_round/quantizer.py:554-759 (lm_head with
+# quant_lm_head=True).  Differences from the block loop: micro-batches of ONE sample with gradient accumulation over the
+# `batch_size` samples of an iteration, MSELoss(reduction="sum"), the FP target is recomputed each step with the FP weight on
+# the FP input, `num_elm` is fixed BEFORE the loop from the first `batch_size` samples (valid tokens when a mask exists,
+# input elements otherwise), and the logged loss of an iteration is the sum of loss.item()/num_elm over its micro-batches.
+# --------------------------------------------------------------------------------------------
+def tune_layer(linear: nn.Linear, fp_inputs, q_inputs, scheme: LayerScheme, iters=200, batch_size=8, lr=None, minmax_lr=None,
+               token_masks=None, enable_minmax_tuning=True, amp=True, amp_dtype=torch.bfloat16, not_use_best_mse=False,
+               sampler=None) -> TuneResult:
+    res = TuneResult()
+    nsamples = len(fp_inputs)
+    dt = linear.weight.dtype
+    fp_inputs = [t.to(dt) for t in fp_inputs]
+    q_inputs = None if q_inputs is None else [t.to(dt) for t in q_inputs]
+    tl = TunableLinear(linear, scheme)
+    base = lr if lr is not None else (2.0 / iters if (iters >= 1000 and scheme.bits <= 3) else 1.0 / iters)
+    groups = [([tl.value], torch.tensor(float(base)))]
+    if enable_minmax_tuning:
+        groups.append(([tl.min_scale, tl.max_scale], torch.tensor(float(minmax_lr if minmax_lr is not None else base))))
+    else:
+        tl.min_scale.requires_grad_(False)
+        tl.max_scale.requires_grad_(False)
+    gas = batch_size                                            # gradient_accumulate_steps = batch_size * 1 (:660-662)
+    gbs = min(nsamples, gas)
+    num_elm = 1
+    if gas != 1:
+        whole = list(range(gbs))
+        if token_masks:
+            num_elm = sum(int(torch.count_nonzero(token_masks[i]).item()) for i in whole)
+        else:
+            src = q_inputs if q_inputs is not None else fp_inputs
+            num_elm = sum(int(src[i].numel()) for i in whole)
+    reduction = "sum" if gas != 1 else "mean"
+    sampler = sampler if sampler is not None else IndexSampler(nsamples, gbs)
+    best_loss = torch.finfo(torch.float).max
+    micro_losses = []
+    for it in range(iters):
+        total = 0.0
+        idx = sampler.next_batch()
+        res.batches.append(list(idx))
+        for i in idx:
+            cur_in = (q_inputs if q_inputs is not None else fp_inputs)[i]
+            org_in = fp_inputs[i]
+            with torch.no_grad():
+                target = linear(org_in)
+            mask = token_masks[i].unsqueeze(-1) if token_masks else None
+            ctx = torch.autocast(device_type="cpu", dtype=amp_dtype) if amp else _null()
+            with ctx:
+                out = tl(cur_in)
+                if mask is not None:
+                    loss = F.mse_loss((out * mask).to(torch.float32), (target * mask).to(torch.float32), reduction=reduction)
+                else:
+                    loss = F.mse_loss(out.to(torch.float32), target.to(torch.float32), reduction=reduction)
+            num_elm = 1 if num_elm <= 0 else num_elm
+            total += loss.item() / num_elm
+            micro_losses.append(float(loss.item()))
+            (loss * 1000).backward()
+        res.losses.append(total)
+        if total < best_loss:
+            best_loss = total
+            if not not_use_best_mse:
+                res.best_params = {k: p.data.clone() for k, p in tl.params.items()}
+                res.best_iter = it
+        if not_use_best_mse and it == iters - 1:
+            res.best_params = {k: p.data.clone() for k, p in tl.params.items()}
+            res.best_iter = it
+        with torch.no_grad():
+            for params, lr_t in groups:
+                for p in params:
+                    if p.grad is not None:
+                        p.add_(torch.sign(p.grad), alpha=-lr_t.item())
+                        p.grad = None
+        for _, lr_t in groups:
+            lr_t.mul_(1.0 + (0.0 - 1.0) / (iters * 1.0 + it * (0.0 - 1.0)))
+    res.best_loss = best_loss
+    res.micro_losses = micro_losses
+    with torch.no_grad():
+        tl.bake(res.best_params)
+    return res
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

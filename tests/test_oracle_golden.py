@@ -209,3 +209,20 @@ def test_index_sampler_is_python_random():
     assert got[0] == idx[:4] and got[1] == idx[4:]
     random.shuffle(idx)
     assert got[2] == idx[:4]
+
+
+def test_tune_layer_lm_head_matches_reference_bit_exact(golden_dir):
+    """quant_lm_head=True -> quantize_layer_outside_block (sign_round/quantizer.py:554-759): every micro-batch loss of the
+    8 iterations and the final lm_head weight / scale."""
+    rec = _load(golden_dir, "lm_head_w4a16_sym_g32.pt")
+    assert len(rec["layers"]) == 1
+    lay = rec["layers"][0]
+    n, k = lay["weight"].shape
+    lin = torch.nn.Linear(k, n, bias=lay["bias"] is not None).to(torch.bfloat16)
+    lin.weight.data.copy_(lay["weight"])
+    masks = [(ids != -100).to(torch.long) for ids in lay["input_ids"]]
+    res = S.tune_layer(lin, lay["fp_inputs"], lay["q_inputs"], S.LayerScheme(4, 32, True, "int"), iters=rec["iters"],
+                       batch_size=rec["batch_size"], token_masks=masks, sampler=S.ReplaySampler(lay["batches"]))
+    assert res.micro_losses == pytest.approx(lay["losses"], rel=1e-6)
+    assert torch.equal(lin.weight.data, lay["out_weight"])
+    assert torch.equal(lin.scale.float().reshape(-1), lay["scale"].float().reshape(-1))
