@@ -659,7 +659,7 @@ class AutoRound:
                         export.pack_layer(n, block, self.quantizer.scheme_for(n, m), self.device)
             self._packed = True
         qcfg = export.build_quantization_config(self.scheme, prefix, None, self.iters, self.nsamples, self.seqlen,
-                                                self.batch_size)
+                                                self.batch_size, tuning=self.sign_kw)
         self.quantization_config = qcfg
         if output_dir is None:
             self.model.config.quantization_config = qcfg

@@ -99,11 +99,25 @@ def pack_layer(name: str, model: nn.Module, scheme: QuantizationScheme, device=N
 
 
 def build_quantization_config(scheme: QuantizationScheme, block_names, extra: Optional[dict] = None, iters=200,
-                              nsamples=128, seqlen=2048, batch_size=8) -> dict:
-    """Keys of export_to_autoround/export.py:286-336 after filter_quantization_config (export/utils.py:334-374)."""
+                              nsamples=128, seqlen=2048, batch_size=8, tuning: Optional[dict] = None) -> dict:
+    """Keys of export_to_autoround/export.py:286-336 after filter_quantization_config (export/utils.py:334-374): a
+    hyper-parameter is written only when it differs from the reference's default (`iters` 200, `lr` / `minmax_lr` 1/iters,
+    `enable_minmax_tuning` / `enable_quanted_input` True); nsamples / seqlen / batch_size are not part of the serialised
+    config in v0.15.0 (pinned by tests/test_export_config.py against configs the reference wrote)."""
     cfg = {"bits": scheme.bits, "group_size": scheme.group_size, "sym": scheme.sym, "data_type": scheme.data_type}
+    tuning = tuning or {}
     if iters == 0:
         cfg["enable_quanted_input"] = False            # RTN route of the reference; the default (True) is filtered out
+    else:
+        if iters != 200:
+            cfg["iters"] = int(iters)
+        default_lr = 1.0 / iters
+        for key in ("lr", "minmax_lr"):
+            if tuning.get(key) is not None and float(tuning[key]) != default_lr:
+                cfg[key] = float(tuning[key])
+        for key in ("enable_minmax_tuning", "enable_quanted_input"):
+            if tuning.get(key) is False:
+                cfg[key] = False
     cfg["static_attention_granularity"] = "tensor"
     cfg["static_kv_granularity"] = "tensor"
     cfg["autoround_version"] = AUTOROUND_VERSION
