@@ -174,9 +174,15 @@ class AutoRound:
         unknown = set(kwargs) - set(_SCHEME_KW) - set(_SIGNROUND_KW)
         if unknown:
             raise TypeError(f"unsupported AutoRound arguments for the B200 hot path: {sorted(unknown)}")
-        for k in ("enable_norm_bias_tuning", "enable_lfq", "quant_lm_head"):
+        for k in ("enable_norm_bias_tuning", "enable_lfq"):
             if kwargs.get(k):
                 raise NotImplementedError(f"{k}=True is outside the B200 hot path")
+        # quant_lm_head: SURVEY.md 8 f4 (quantize_layer_outside_block).  Oracle pinned against a reference run
+        # (tests/golden/lm_head_*.pt); the CUDA loop (quantizer.quantize_layer) has not run on hardware yet -> same switch as alg_ext
+        self.quant_lm_head = bool(kwargs.get("quant_lm_head"))
+        if self.quant_lm_head and os.environ.get("AR_B200_UNVERIFIED", "0") != "1":
+            raise NotImplementedError("quant_lm_head=True: layer tuning outside the blocks is not yet validated on a B200 "
+                                      "(set AR_B200_UNVERIFIED=1 to run it)")
         if kwargs.get("dynamic_max_gap", -1) not in (-1, None) or kwargs.get("momentum") not in (None, 0, 0.0):
             raise NotImplementedError("dynamic_max_gap / momentum: only the reference defaults (-1 / 0)")
         if kwargs.get("nblocks", 1) != 1:
@@ -493,7 +499,7 @@ class AutoRound:
             res = quantizer.last_result
             ev[2].record()
             # (6) outputs of the quantised block feed the next block (composer.py:476-481)
-            if quantizer.enable_quanted_input and bi + 1 < nblk:
+            if quantizer.enable_quanted_input and (bi + 1 < nblk or self.quant_lm_head):
                 q_inputs = self._forward_all(quantizer, block, eff, others, token_masks)
             else:
                 q_inputs = None
@@ -516,6 +522,9 @@ class AutoRound:
             self.block_results.append({"block": f"{prefix}.{bi}", "init_loss": res.init_loss, "best_loss": res.best_loss,
                                        "best_iter": res.best_iter, "seconds": time.time() - tb, "losses": res.losses,
                                        "phases_ms": phases, "cuda_graph": res.used_cuda_graph})
+        self._lm_head_extra = None
+        if self.quant_lm_head:
+            self._quantize_lm_head(quantizer, fp_inputs, q_inputs, ids_cache)
         self.timings["tuning_s"] = time.time() - t0                      # "quantization tuning time" (orchestrator.py:792)
         if resume is not None and self.dp.rank == 0:
             resume.clear()                                                # a finished run leaves no state behind
@@ -529,6 +538,47 @@ class AutoRound:
                     layer_cfg[f"{prefix}.{bi}.{n}"] = self.scheme.to_dict()
         self.layer_config_out = layer_cfg
         return model, layer_cfg
+
+    def _find_tail(self):
+        """(final norm module, output projection, its name) of a causal LM: the layers between the last block and the
+        logits.  The reference discovers them with hooks on a full-model forward (orchestrator.py:549-592); here the
+        block chain already holds the last block's outputs, so only the norm in between has to be applied."""
+        model = self.model
+        if getattr(getattr(model, "config", None), "tie_word_embeddings", False):
+            raise NotImplementedError("quant_lm_head with tied input/output embeddings")
+        head = getattr(model, "lm_head", None)
+        if not isinstance(head, nn.Linear):
+            raise NotImplementedError("quant_lm_head: the model has no nn.Linear `lm_head`")
+        for path in ("model.norm", "model.final_layernorm", "transformer.ln_f", "model.decoder.final_layer_norm"):
+            try:
+                return model.get_submodule(path), head, "lm_head"
+            except AttributeError:
+                continue
+        raise NotImplementedError("quant_lm_head: cannot locate the final normalisation layer of this architecture")
+
+    def _quantize_lm_head(self, quantizer, fp_chain, q_chain, ids_cache):
+        """orchestrator.py:840-930 -> quantize_layer_outside_block: tune lm_head on (norm(q chain), norm(FP chain))."""
+        norm, head, name = self._find_tail()
+        norm.to(self.device)
+        head.to(self.device)
+        for p in list(norm.parameters()) + list(head.parameters()):
+            p.requires_grad_(False)
+            if p.dtype in (torch.float32, torch.float16):
+                p.data = p.data.to(self.amp_dtype)
+        with torch.no_grad(), torch.autocast(device_type="cuda", dtype=self.amp_dtype):
+            fp_h = [norm(t.to(self.device)).to(self.amp_dtype) for t in fp_chain]
+            q_h = None if q_chain is None else [norm(t.to(self.device)).to(self.amp_dtype) for t in q_chain]
+        sc = quantizer.scheme_for(name, head)
+        gs = ops.nv_global_scale(head.weight.data.contiguous()) if sc.qdq_name == "nv_fp4" else None
+        quantizer.quantize_layer(head, fp_h, q_h, input_ids=ids_cache, name=name, nv_global_scale=gs)
+        res = quantizer.last_result
+        self.block_results.append({"block": name, "init_loss": res.init_loss, "best_loss": res.best_loss,
+                                   "best_iter": res.best_iter, "losses": res.losses})
+        if self._pack_on_the_fly:
+            export.pack_layer(name, self.model, sc, self.device, out_device=self.device)
+        self._lm_head_extra = {name: export.extra_config_entry(sc)}
+        norm.to("cpu")
+        self.model.get_submodule(name).to("cpu")
 
     def _open_resume(self, prefix: str, blocks):
         """-> (ResumeState | None, index of the first block still to do).  Active only when AR_RESUME_DIR is set."""
@@ -658,8 +708,8 @@ class AutoRound:
                     if type(m) is nn.Linear and hasattr(m, "scale"):
                         export.pack_layer(n, block, self.quantizer.scheme_for(n, m), self.device)
             self._packed = True
-        qcfg = export.build_quantization_config(self.scheme, prefix, None, self.iters, self.nsamples, self.seqlen,
-                                                self.batch_size, tuning=self.sign_kw)
+        qcfg = export.build_quantization_config(self.scheme, prefix, getattr(self, "_lm_head_extra", None), self.iters,
+                                                self.nsamples, self.seqlen, self.batch_size, tuning=self.sign_kw)
         self.quantization_config = qcfg
         if output_dir is None:
             self.model.config.quantization_config = qcfg

@@ -98,6 +98,15 @@ def pack_layer(name: str, model: nn.Module, scheme: QuantizationScheme, device=N
     return ql
 
 
+def extra_config_entry(scheme: QuantizationScheme) -> dict:
+    """`extra_config[layer]` of a quantised layer outside the blocks (lm_head): every QuantizationScheme field of the
+    resolved per-layer config (export_to_autoround/export.py:303-306).  For the weight-only schemes in scope the reference
+    resolves the activation fields to their defaults (16 bit float, dynamic, symmetric, the weight's group size)."""
+    return {"act_bits": 16, "act_data_type": "float", "act_dynamic": True, "act_group_size": scheme.group_size, "act_sym": True,
+            "bits": scheme.bits, "data_type": scheme.data_type, "group_size": scheme.group_size, "rotation_config": None,
+            "super_bits": None, "super_group_size": None, "sym": scheme.sym}
+
+
 def build_quantization_config(scheme: QuantizationScheme, block_names, extra: Optional[dict] = None, iters=200,
                               nsamples=128, seqlen=2048, batch_size=8, tuning: Optional[dict] = None) -> dict:
     """Keys of export_to_autoround/export.py:286-336 after filter_quantization_config (export/utils.py:334-374): a

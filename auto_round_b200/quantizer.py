@@ -503,6 +503,97 @@ class SignRoundQuantizer:
         return {n: arena.best_views(n) for n in wrapped}
 
 
+    # ---------------------------------------------------------------------------------------------
+    def quantize_layer(self, layer: nn.Linear, fp_inputs, q_inputs=None, input_ids=None, name: str = "lm_head", **kwargs):
+        """A linear OUTSIDE the block list (lm_head with `quant_lm_head=True`) -- mirror of
+        SignRoundQuantizer.quantize_layer_outside_block (sign_round/quantizer.py:554-759).  Differences from the block loop,
+        all the reference's: micro-batches of one sample with the gradient accumulated over the `batch_size` samples of an
+        iteration (the fused grad-w epilogue runs with accumulate=1), MSELoss(reduction="sum"), the target is the FP weight
+        applied to the FP input (recomputed each step: 128 x [2048, 128256] bf16 targets would be 67 GB for Llama-3), the
+        tuning forward reads the quantised-chain input when there is one, and `num_elm` is fixed before the loop from the
+        first `batch_size` samples.  `fp_inputs` / `q_inputs`: lists of [1, S, K] tensors.  Mutates `layer` in place."""
+        device = layer.weight.device
+        if not layer.weight.is_cuda:
+            raise RuntimeError("quantize_layer: the layer must be on a CUDA device (no CPU tuning path)")
+        if self.dp.world > 1:
+            raise NotImplementedError("quantize_layer under data parallelism (every rank would repeat the same work)")
+        sc = self.scheme_for(name, layer)
+        n, k = layer.weight.shape
+        spec = ops.make_spec(sc.qdq_name, sc.bits, sc.group_size, n, k, 1e-5, 1.0)
+        arena = TuneArena({name: spec}, device, torch.float32)
+        gs = kwargs.get("nv_global_scale")
+        wl = WrapperLinear(layer, sc, spec, arena.layer_views(name), gs)
+        nsamples = len(fp_inputs)
+        fp_all = self._stack(fp_inputs, device).to(torch.bfloat16)
+        seq = fp_all.shape[1]
+        fp_all = fp_all.reshape(nsamples, seq, k).contiguous()
+        q_all = None if q_inputs is None else self._stack(q_inputs, device).to(torch.bfloat16).reshape(nsamples, seq, k).contiguous()
+        token_masks = None
+        if input_ids is not None:
+            masks = [(ids != -100).reshape(-1) for ids in input_ids]
+            if not all(bool(m.all()) for m in masks):
+                token_masks = torch.stack(masks).to(device=device, dtype=torch.uint8).contiguous()
+        iters = self.iters
+        gbs = min(nsamples, self.batch_size)                       # gradient_accumulate_steps = batch_size (:660-662)
+        if self.batch_size != 1:
+            if token_masks is not None:
+                num_elm = int(token_masks[:gbs].sum())
+            else:
+                num_elm = gbs * seq * k                            # _count_layer_input_elements over the first gbs samples
+            inv_numel = 1.0                                        # reduction="sum"
+        else:
+            num_elm, inv_numel = 1, 1.0 / float(seq * n)
+        num_elm = 1 if num_elm <= 0 else num_elm
+        sampler = kwargs.get("sampler") or IndexSampler(nsamples, gbs)
+        batches = [list(sampler.next_batch()) for _ in range(iters)]
+        res = TuneResult(quantized_layers=[name], batches=batches)
+        self.last_result = res
+        lr0 = self.compute_lr(sc.bits)
+        mm_lr0 = float(self.minmax_lr) if self.minmax_lr is not None else lr0
+        if not self.enable_minmax_tuning:
+            mm_lr0 = 0.0
+        lr_tab = torch.from_numpy(lr_schedule_table(iters, lr0, mm_lr0)).to(device).reshape(-1)
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=device)
+        state = torch.zeros(4, dtype=torch.float64, device=device)
+        flag = torch.zeros(1, dtype=torch.int32, device=device)
+        hist = torch.zeros(max(iters, 1), dtype=torch.float32, device=device)
+        w, bias = wl.weight, wl.bias_bf16
+        target = torch.empty(seq, n, dtype=torch.bfloat16, device=device)
+        pred = torch.empty_like(target)
+        dpred = torch.empty_like(target)
+        for it in range(iters):
+            for j, i in enumerate(batches[it]):
+                cur = (q_all if q_all is not None else fp_all)[i]
+                ops.gemm(fp_all[i], w, bias=bias, out=target)                                   # layer(org_input), no grad
+                if j == 0:                                          # parameters are fixed inside an iteration: one qdq
+                    ops.fq_linear_fwd(spec, cur, w, wl.value, wl.min_scale, wl.max_scale, wl.weight_min, wl.weight_max,
+                                      wl.weight_global_scale, bias, wl.wq, out=pred)
+                else:
+                    ops.gemm(cur, wl.wq, bias=bias, out=pred)
+                ops.mse_fwd_bwd(pred, target, None if token_masks is None else token_masks[i], inv_numel, 1000.0, loss_sum,
+                                dpred=dpred)
+                ops.fq_linear_bwd_dw(spec, dpred, cur, w, wl.value, wl.min_scale, wl.max_scale, wl.weight_min, wl.weight_max,
+                                     wl.weight_global_scale, wl.grad_value, wl.grad_min_scale, wl.grad_max_scale,
+                                     accumulate=(j > 0))
+            ops.best_update(loss_sum, inv_numel, 1.0 / float(num_elm), it, state, flag, hist)
+            if self.not_use_best_mse:
+                flag.fill_(1 if it == iters - 1 else 0)
+            ops.signsgd_step(arena.params, arena.grads_v, arena.best, flag, lr_tab, it, arena.clamp_begin, 1.0,
+                             g_scales=arena.grads_s)
+        if iters > 0:
+            st = state.cpu().tolist()
+            res.losses = hist.cpu().tolist()[:iters]
+            res.best_loss, res.best_iter, res.init_loss = st[0], int(st[2]), res.losses[0]
+            if self.not_use_best_mse:
+                res.best_iter, res.best_loss = iters - 1, res.losses[-1]
+            with torch.no_grad():
+                lin = wl.unwrapper(arena.best_views(name))
+        else:
+            with torch.no_grad():
+                lin = wl.unwrapper({})
+        return lin
+
+
 def _to_device(v, device):
     if isinstance(v, torch.Tensor):
         return v.to(device)
