@@ -1,8 +1,8 @@
 """enable_alg_ext on the GPU: searched init scale, max_scale in [0, 2], outlier-suppressed loss.
 
-STATUS: written after round 1's GPU budget was spent -- the CPU side (oracle + the four reference fixtures
-tests/golden/block_algext_*.pt, tests/test_oracle_golden.py) is pinned bit-exact, the CUDA side has compiled but NOT run
-on hardware yet.  The tests therefore only run when AR_B200_UNVERIFIED=1 (the same switch the product path asks for);
+STATUS: written when round 1's GPU budget was almost spent -- the CPU side (oracle + the four reference fixtures
+tests/golden/block_algext_*.pt, tests/test_oracle_golden.py) is pinned bit-exact and the kernels passed the torch-free
+tools/gpu_selftest on the B200 (profiles/r01_gpu_selftest.txt), but this file (and the loop it drives) has NOT run yet.  The tests therefore only run when AR_B200_UNVERIFIED=1 (the same switch the product path asks for);
 the first GPU session of the next round runs them with the switch, fixes what they find and removes the gate.
 
 What they state (same bars as tests/test_gpu_kernels.py / test_gpu_engine.py):
