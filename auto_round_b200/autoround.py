@@ -194,8 +194,10 @@ class AutoRound:
         # The symmetric route (searched init scale, max_scale in [0,2], outlier-suppressed loss) is written and pinned on the
         # CPU side (oracle + tests/golden/block_algext_*.pt) but its CUDA path has not run on hardware yet, so it has to be
         # asked for explicitly; without the switch the request fails loudly instead of running unvalidated numerics.
-        self.enable_alg_ext = bool(kwargs.get("enable_alg_ext")) and self.scheme.qdq_name != "int_asym"
-        if self.enable_alg_ext and os.environ.get("AR_B200_UNVERIFIED", "0") != "1":
+        # For int asym the only effect is the loss: SignRoundV2Quantizer._get_loss falls back to the base MSE without the
+        # valid-token mask (sign_roundv2/quantizer.py:399), which the fixtures confirm -- mirrored, not gated (same kernels).
+        self.enable_alg_ext = bool(kwargs.get("enable_alg_ext"))
+        if self.enable_alg_ext and self.scheme.qdq_name != "int_asym" and os.environ.get("AR_B200_UNVERIFIED", "0") != "1":
             raise NotImplementedError("enable_alg_ext for symmetric schemes: CUDA path not yet validated on a B200 "
                                       "(set AR_B200_UNVERIFIED=1 to run it; tests/test_gpu_alg_ext.py holds its parity tests)")
         self.layer_config = layer_config or {}
@@ -485,7 +487,8 @@ class AutoRound:
             ev[0].record()
             # (3) reference outputs of the FP block on the FP inputs  (composer.py:423-429)
             imatrices = None
-            if self.enable_alg_ext:     # imatrix hooks on the FP-input forward, raw sums (sign_roundv2/quantizer.py:401-428)
+            if self.enable_alg_ext and self.scheme.qdq_name != "int_asym":   # imatrix hooks on the FP-input forward, raw
+                # sums (sign_roundv2/quantizer.py:401-428); the reference collects them for asym too but never reads them
                 with _collect_imatrix(block, names, self.device) as col:
                     ref_out = self._forward_all(quantizer, block, fp_inputs, others, token_masks)
                 imatrices = col.finish(self.dp, normalise=False)

@@ -394,9 +394,11 @@ class SignRoundQuantizer:
 
         # enable_alg_ext loss (SignRoundV2Quantizer._get_loss, sign_roundv2/quantizer.py:362-399): bits < 4 -> the numel/1000
         # largest |pred - ref| are dropped; otherwise it falls back to the base MSE WITHOUT forwarding the valid-token mask
+        # (sign_roundv2/quantizer.py:399).  That fallback also applies to int asym, which keeps the plain wrapper: with
+        # enable_alg_ext its loss runs over every token (pinned by tests/golden/block_algext_w2a16_asym_g32.pt).
         optimized = [wl for wl in wrapped.values() if wl.init_scale is not None]
         outlier_loss = bool(optimized) and self.scheme.sym and self.scheme.bits < 4
-        unmasked_loss = bool(optimized) and not outlier_loss
+        unmasked_loss = self.enable_alg_ext and not outlier_loss
         clamp_hi = 2.0 if optimized else 1.0                        # minmax_scale_bound (sign_roundv2/quantizer.py:102)
         if optimized and len(optimized) != len(wrapped):
             raise NotImplementedError("enable_alg_ext with mixed optimized / plain layers in one block (per-layer bounds)")

@@ -138,6 +138,7 @@ ALGEXT = {
     "algext_w4a16_sym_g32": (dict(scheme="W4A16", group_size=32), S.LayerScheme(4, 32, True, "int")),
     "algext_mxfp4": (dict(scheme="MXFP4", act_bits=16), S.LayerScheme(4, 32, True, "mx_fp")),
     "algext_nvfp4": (dict(scheme="NVFP4", act_bits=16, act_data_type="float"), S.LayerScheme(4, 16, True, "nv_fp")),
+    "algext_w2a16_asym_g32": (dict(scheme="W2A16", group_size=32, sym=False), S.LayerScheme(2, 32, False, "int")),
 }
 
 

@@ -173,6 +173,8 @@ ALGEXT = {
     "algext_w4a16_sym_g32": S.LayerScheme(4, 32, True, "int"),      # init scale only
     "algext_mxfp4": S.LayerScheme(4, 32, True, "mx_fp"),
     "algext_nvfp4": S.LayerScheme(4, 16, True, "nv_fp"),
+    # int asym keeps the plain wrapper; the only effect of enable_alg_ext is the loss over ALL tokens (BASELINE config 3)
+    "algext_w2a16_asym_g32": S.LayerScheme(2, 32, False, "int"),
 }
 
 
