@@ -228,3 +228,22 @@ def test_tune_layer_lm_head_matches_reference_bit_exact(golden_dir):
     assert res.micro_losses == pytest.approx(lay["losses"], rel=1e-6)
     assert torch.equal(lin.weight.data, lay["out_weight"])
     assert torch.equal(lin.scale.float().reshape(-1), lay["scale"].float().reshape(-1))
+
+
+def test_iters1000_low_bit_lr_rule_matches_reference(golden_dir):
+    """BASELINE.json config 3 hyper-parameters on the tiny Llama: W2A16 asym g32, enable_alg_ext, iters=1000 -> lr = 2/iters
+    (bits <= 3 and iters >= 1000, sign_round/config.py:107-136), LinearLR over 1000 steps in the lr tensor's fp32, loss over
+    every token.  All 1000 losses and the final weights of block 0, bit for bit."""
+    rec = _load(golden_dir, "block_w2a16_asym_g32_iters1000.pt")
+    assert rec["iters"] == 1000
+    sc = S.LayerScheme(2, 32, False, "int")
+    b = rec["blocks"][0]
+    blk = _tiny_block(b["block_state"])
+    masks = [(ids != -100).to(torch.long) for ids in b["input_ids"]]
+    res = S.tune_block(blk, b["inputs"], b["others"], b["fp_outputs"], lambda n, m: sc, iters=1000, batch_size=rec["batch_size"],
+                       token_masks=masks, sampler=S.ReplaySampler(b["batches"]), alg_ext=True, imatrices=b["imatrix"])
+    nvalid = [sum(int(masks[i].sum()) for i in batch) for batch in b["batches"]]
+    got = [l * n for l, n in zip(res.losses, nvalid)]
+    assert got == pytest.approx(b["losses"], rel=1e-6)
+    for name, lay in b["layers"].items():
+        assert torch.equal(blk.get_submodule(name).weight.data, lay["weight"]), name
