@@ -162,13 +162,31 @@ def tiny_llama(seed=0, layers=2, hidden=64, inter=128, heads=4, kv=2, vocab=128)
     return m
 
 
-def gen_block(tag, scheme_kwargs, iters=8, nsamples=8, seqlen=16, batch_size=4):
+def tiny_opt(seed=0):
+    from transformers import OPTConfig, OPTForCausalLM
+
+    torch.manual_seed(seed)
+    cfg = OPTConfig(hidden_size=64, ffn_dim=128, num_hidden_layers=2, num_attention_heads=4, vocab_size=128,
+                    max_position_embeddings=64, word_embed_proj_dim=64)
+    return OPTForCausalLM(cfg).to(torch.bfloat16).eval()
+
+
+def tiny_qwen2(seed=0):
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+
+    torch.manual_seed(seed)
+    cfg = Qwen2Config(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, vocab_size=128, max_position_embeddings=64, tie_word_embeddings=False)
+    return Qwen2ForCausalLM(cfg).to(torch.bfloat16).eval()
+
+
+def gen_block(tag, scheme_kwargs, iters=8, nsamples=8, seqlen=16, batch_size=4, model_factory=None):
     import auto_round.algorithms.quantization.sign_round.quantizer as qz
     import auto_round.compressors.utils as cu
     from auto_round import AutoRound
     from oracle.ref_shim import DummyTokenizer
 
-    model = tiny_llama()
+    model = (model_factory or tiny_llama)()
     init_state = {k: v.clone() for k, v in model.state_dict().items()}
     tokens = torch.randint(0, 128, (nsamples, seqlen), generator=torch.Generator().manual_seed(1))
     dataset = [tokens[i:i + batch_size] for i in range(0, nsamples, batch_size)]
@@ -298,6 +316,10 @@ def main(argv):
         gen_block("w2a16_asym_g32", dict(scheme="W2A16", group_size=32, sym=False))
         gen_block("nvfp4", dict(scheme="NVFP4", act_bits=16, act_data_type="float"))
         gen_block("mxfp4", dict(scheme="MXFP4", act_bits=16))
+    if "arch" in what:
+        # other architectures of BASELINE.json's configs: OPT (LayerNorm / ReLU / biases / learned positions) and Qwen2 (q/k/v bias)
+        gen_block("opt_w4a16_sym_g32", dict(scheme="W4A16", group_size=32), model_factory=tiny_opt)
+        gen_block("qwen2_nvfp4", dict(scheme="NVFP4", act_bits=16, act_data_type="float"), model_factory=tiny_qwen2)
     if "algext" in what:
         # enable_alg_ext (sign_roundv2): searched init_scale, max_scale in [0,2]; outlier-masked loss when bits < 4
         gen_block("algext_w2a16_sym_g32", dict(scheme="W2A16", group_size=32, enable_alg_ext=True))

@@ -247,3 +247,47 @@ def test_iters1000_low_bit_lr_rule_matches_reference(golden_dir):
     assert got == pytest.approx(b["losses"], rel=1e-6)
     for name, lay in b["layers"].items():
         assert torch.equal(blk.get_submodule(name).weight.data, lay["weight"]), name
+
+
+def _arch_block(arch, state):
+    """Decoder layer of the tiny OPT / Qwen2 the fixtures were generated on (oracle/gen_golden.py tiny_opt / tiny_qwen2)."""
+    if arch == "opt":
+        from transformers import OPTConfig
+        from transformers.models.opt.modeling_opt import OPTDecoderLayer
+
+        cfg = OPTConfig(hidden_size=64, ffn_dim=128, num_hidden_layers=2, num_attention_heads=4, vocab_size=128,
+                        max_position_embeddings=64, word_embed_proj_dim=64)
+        cfg._attn_implementation = "sdpa"
+        blk = OPTDecoderLayer(cfg, layer_idx=0)
+    else:
+        from transformers import Qwen2Config
+        from transformers.models.qwen2.modeling_qwen2 import Qwen2DecoderLayer
+
+        cfg = Qwen2Config(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                          num_key_value_heads=2, vocab_size=128, max_position_embeddings=64, tie_word_embeddings=False)
+        cfg._attn_implementation = "sdpa"
+        blk = Qwen2DecoderLayer(cfg, 0)
+    blk = blk.to(torch.bfloat16).eval()
+    blk.load_state_dict(state)
+    return blk
+
+
+@pytest.mark.parametrize("arch,tag,sc", [("opt", "opt_w4a16_sym_g32", S.LayerScheme(4, 32, True, "int")),
+                                          ("qwen2", "qwen2_nvfp4", S.LayerScheme(4, 16, True, "nv_fp"))])
+def test_tune_block_other_architectures_match_reference_bit_exact(golden_dir, arch, tag, sc):
+    """BASELINE.json configs 0 and 3: OPT (LayerNorm, ReLU, biases, attention-mask-only kwargs) and Qwen2 (q/k/v bias, NVFP4
+    with the fused q/k/v and gate/up global scales) through the same oracle loop."""
+    rec = _load(golden_dir, f"block_{tag}.pt")
+    for b in rec["blocks"]:
+        blk = _arch_block(arch, b["block_state"])
+        masks = [(ids != -100).to(torch.long) for ids in b["input_ids"]]
+        res = S.tune_block(blk, b["inputs"], b["others"], b["fp_outputs"], lambda n, m: sc, iters=rec["iters"],
+                           batch_size=rec["batch_size"], token_masks=masks, nv_global_scales=b["nv_gs"] or None,
+                           sampler=S.ReplaySampler(b["batches"]))
+        nvalid = [sum(int(masks[i].sum()) for i in batch) for batch in b["batches"]]
+        got = [l * n for l, n in zip(res.losses, nvalid)]
+        assert got == pytest.approx(b["losses"], rel=1e-6)
+        for name, lay in b["layers"].items():
+            mod = blk.get_submodule(name)
+            assert torch.equal(mod.weight.data, lay["weight"]), (tag, name)
+            assert torch.equal(mod.scale.float().reshape(-1), lay["scale"].float().reshape(-1)), (tag, name)
