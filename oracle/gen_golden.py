@@ -180,6 +180,20 @@ def tiny_qwen2(seed=0):
     return Qwen2ForCausalLM(cfg).to(torch.bfloat16).eval()
 
 
+def tiny_mixtral(seed=0):
+    from transformers import MixtralConfig, MixtralForCausalLM
+
+    torch.manual_seed(seed)
+    cfg = MixtralConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                        num_key_value_heads=2, vocab_size=128, max_position_embeddings=64, num_local_experts=4,
+                        num_experts_per_tok=2, tie_word_embeddings=False)
+    m = MixtralForCausalLM(cfg).to(torch.bfloat16).eval()
+    for p in m.parameters():              # HF leaves the fused 3-D expert parameters uninitialised-small: give them signal
+        if p.dim() >= 2:
+            p.data.normal_(0, 0.05)
+    return m
+
+
 def gen_block(tag, scheme_kwargs, iters=8, nsamples=8, seqlen=16, batch_size=4, model_factory=None):
     import auto_round.algorithms.quantization.sign_round.quantizer as qz
     import auto_round.compressors.utils as cu
@@ -320,6 +334,7 @@ def main(argv):
         # other architectures of BASELINE.json's configs: OPT (LayerNorm / ReLU / biases / learned positions) and Qwen2 (q/k/v bias)
         gen_block("opt_w4a16_sym_g32", dict(scheme="W4A16", group_size=32), model_factory=tiny_opt)
         gen_block("qwen2_nvfp4", dict(scheme="NVFP4", act_bits=16, act_data_type="float"), model_factory=tiny_qwen2)
+        gen_block("mixtral_mxfp4", dict(scheme="MXFP4", act_bits=16), model_factory=tiny_mixtral)
     if "algext" in what:
         # enable_alg_ext (sign_roundv2): searched init_scale, max_scale in [0,2]; outlier-masked loss when bits < 4
         gen_block("algext_w2a16_sym_g32", dict(scheme="W2A16", group_size=32, enable_alg_ext=True))

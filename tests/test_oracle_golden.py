@@ -291,3 +291,36 @@ def test_tune_block_other_architectures_match_reference_bit_exact(golden_dir, ar
             mod = blk.get_submodule(name)
             assert torch.equal(mod.weight.data, lay["weight"]), (tag, name)
             assert torch.equal(mod.scale.float().reshape(-1), lay["scale"].float().reshape(-1)), (tag, name)
+
+
+def test_tune_block_mixtral_moe_matches_reference_bit_exact(golden_dir):
+    """BASELINE.json config 5 (Mixtral, MXFP4 weight-only) on a tiny 4-expert block: the reference un-fuses the fused 3-D
+    expert parameters into per-expert linears (modeling/fused_moe/moe_experts_interface.py:173-260).  The block here is built
+    with the PRODUCT's host-side un-fusing (auto_round_b200/moe.py, pure torch), so a bit-exact replay of the reference's
+    8 iterations pins that module and the oracle loop on ragged expert batches (experts that see no token get no update)."""
+    from transformers import MixtralConfig
+    from transformers.models.mixtral.modeling_mixtral import MixtralDecoderLayer
+
+    from auto_round_b200.moe import unfuse_experts
+
+    rec = _load(golden_dir, "block_mixtral_mxfp4.pt")
+    sc = S.LayerScheme(4, 32, True, "mx_fp")
+    cfg = MixtralConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                        num_key_value_heads=2, vocab_size=128, max_position_embeddings=64, num_local_experts=4,
+                        num_experts_per_tok=2, tie_word_embeddings=False)
+    cfg._attn_implementation = "sdpa"
+    for b in rec["blocks"]:
+        blk = MixtralDecoderLayer(cfg, 0).to(torch.bfloat16).eval()
+        assert unfuse_experts(blk) == 1
+        blk.load_state_dict(b["block_state"])
+        masks = [(ids != -100).to(torch.long) for ids in b["input_ids"]]
+        res = S.tune_block(blk, b["inputs"], b["others"], b["fp_outputs"], lambda n, m: sc, iters=rec["iters"],
+                           batch_size=rec["batch_size"], token_masks=masks, sampler=S.ReplaySampler(b["batches"]))
+        assert len(b["layers"]) == 16
+        nvalid = [sum(int(masks[i].sum()) for i in batch) for batch in b["batches"]]
+        got = [l * n for l, n in zip(res.losses, nvalid)]
+        assert got == pytest.approx(b["losses"], rel=1e-6)
+        for name, lay in b["layers"].items():
+            mod = blk.get_submodule(name)
+            assert torch.equal(mod.weight.data, lay["weight"]), name
+            assert torch.equal(mod.scale.float().reshape(-1), lay["scale"].float().reshape(-1)), name
