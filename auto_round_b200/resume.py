@@ -32,69 +32,64 @@ FP_INPUT = "resume_input_ids.pt"      # the reference's name for the chained ful
 _SCALARS = (int, float, bool, str, type(None))
 
 
-def _to_cpu(obj):
-    if isinstance(obj, torch.Tensor):
-        return obj.detach().to("cpu")
-    if isinstance(obj, dict):
-        return {k: _to_cpu(v) for k, v in obj.items()}
-    if isinstance(obj, (list, tuple)):
-        return type(obj)(_to_cpu(v) for v in obj)
-    return obj
+def host_copy(tree):
+    """Detached CPU copy of every tensor in a (possibly nested) list / tuple / dict; other leaves pass through."""
+    if torch.is_tensor(tree):
+        return tree.detach().cpu()
+    if isinstance(tree, dict):
+        return {key: host_copy(val) for key, val in tree.items()}
+    if isinstance(tree, (list, tuple)):
+        return type(tree)(map(host_copy, tree))
+    return tree
+
+
+_to_cpu = host_copy
+
+
+def _write_atomically(target: Path, emit, binary: bool) -> None:
+    """Write through a temporary sibling and rename it over `target`, so that a crash never leaves a torn file."""
+    handle, scratch = tempfile.mkstemp(dir=str(target.parent), prefix=".tmp_resume_")
+    try:
+        with os.fdopen(handle, "wb" if binary else "w") as stream:     # a stream, not a path: torch.save names its archive
+            emit(stream)                                                # after the path otherwise
+        os.replace(scratch, target)
+    except BaseException:
+        if os.path.exists(scratch):
+            os.remove(scratch)
+        raise
 
 
 def _atomic_write_json(path: Path, data: dict) -> None:
-    fd, tmp = tempfile.mkstemp(dir=str(path.parent), prefix=".tmp_resume_")
-    try:
-        with os.fdopen(fd, "w") as f:
-            json.dump(data, f)
-        os.replace(tmp, path)
-    except Exception:
-        try:
-            os.remove(tmp)
-        except OSError:
-            pass
-        raise
+    _write_atomically(path, lambda stream: json.dump(data, stream), binary=False)
 
 
 def _atomic_save(obj, path: Path) -> None:
-    fd, tmp = tempfile.mkstemp(dir=str(path.parent), prefix=".tmp_resume_")
-    try:
-        with os.fdopen(fd, "wb") as f:                 # a file object: torch.save derives archive names from paths otherwise
-            torch.save(obj, f)
-        os.replace(tmp, path)
-    except Exception:
-        try:
-            os.remove(tmp)
-        except OSError:
-            pass
-        raise
+    _write_atomically(path, lambda stream: torch.save(obj, stream), binary=True)
+
+
+def _scalar_items(cfg: dict):
+    for key in sorted(cfg, key=str):
+        if isinstance(cfg[key], _SCALARS):
+            yield f"{key}={cfg[key]}"
 
 
 def layer_config_fingerprint(layer_config) -> str:
-    """utils/resume.py:185-222: scalar per-layer settings only, deterministic order."""
+    """Same string as utils/resume.py:185-222 builds: per layer (sorted) its scalar settings (sorted), nothing else."""
     if not layer_config:
         return "<no-layer-config>"
-    parts = []
-    for name in sorted(layer_config):
-        cfg = layer_config[name]
-        if hasattr(cfg, "to_dict"):
-            cfg = cfg.to_dict()
-        if isinstance(cfg, dict):
-            desc = ",".join(f"{k}={v}" for k, v in sorted(cfg.items(), key=lambda kv: str(kv[0])) if isinstance(v, _SCALARS))
-        else:
-            desc = str(cfg)
-        parts.append(f"{name}:{desc}")
-    return ";".join(parts)
+    rows = []
+    for layer in sorted(layer_config):
+        cfg = layer_config[layer]
+        cfg = cfg.to_dict() if hasattr(cfg, "to_dict") else cfg
+        rows.append(f"{layer}:" + (",".join(_scalar_items(cfg)) if isinstance(cfg, dict) else str(cfg)))
+    return ";".join(rows)
 
 
 def compute_run_signature(model_id: Optional[str], scheme_desc: str, dataset_desc: str, nsamples: int, seqlen: int,
                           block_names: list) -> str:
-    """utils/resume.py:166-182."""
-    h = hashlib.sha256()
-    for part in (model_id or "", scheme_desc, dataset_desc, str(nsamples), str(seqlen), "|".join(block_names)):
-        h.update(part.encode("utf-8"))
-        h.update(b"\x00")
-    return h.hexdigest()
+    """sha256 over the NUL-terminated identifying strings -- the digest utils/resume.py:166-182 produces."""
+    fields_ = (model_id or "", scheme_desc, dataset_desc, str(nsamples), str(seqlen), "|".join(block_names))
+    return hashlib.sha256(b"".join(f.encode("utf-8") + b"\x00" for f in fields_)).hexdigest()
 
 
 def dataset_fingerprint(dataset) -> str:
@@ -170,22 +165,22 @@ class ResumeState:
     def _block_path(self, name: str) -> Path:
         return self.dir / ("block_" + name.replace("/", "_") + ".pt")
 
-    def _load(self) -> None:
-        if not self.manifest_path.exists():
-            return
+    def _trusted_prefix(self) -> list:
+        """The finished blocks a manifest may vouch for: same run signature, a PREFIX of the current block order
+        (utils/resume.py:96-119), and every result file still on disk.  Anything else means "start from block 0"."""
         try:
-            with open(self.manifest_path) as f:
-                data = json.load(f)
-        except Exception:  # noqa: BLE001 -- a corrupt manifest means "start fresh", like the reference
-            return
-        if data.get("signature") != self.signature:
-            return
-        completed = data.get("completed_blocks", [])
-        if completed != self.block_names[: len(completed)]:
-            return
-        if not all(self._block_path(n).exists() for n in completed):
-            return                                   # a result file is missing: the manifest overstates what is durable
-        self.completed_blocks = list(completed)
+            manifest = json.loads(self.manifest_path.read_text())
+        except (OSError, ValueError):
+            return []
+        if manifest.get("signature") != self.signature:
+            return []
+        done = list(manifest.get("completed_blocks", []))
+        if done != self.block_names[:len(done)]:
+            return []
+        return done if all(self._block_path(name).exists() for name in done) else []
+
+    def _load(self) -> None:
+        self.completed_blocks = self._trusted_prefix()
 
     @property
     def resume_index(self) -> int:
