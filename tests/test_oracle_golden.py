@@ -324,3 +324,30 @@ def test_tune_block_mixtral_moe_matches_reference_bit_exact(golden_dir):
             mod = blk.get_submodule(name)
             assert torch.equal(mod.weight.data, lay["weight"]), name
             assert torch.equal(mod.scale.float().reshape(-1), lay["scale"].float().reshape(-1)), name
+
+
+def test_reference_ste_and_reshape_unit_tests_on_the_oracle():
+    """The assertions of the reference's own test/unit/test_cuda/data_type/test_ste.py (grad flow through the straight-through
+    helpers, pad / revert of the group reshape for group sizes 4, 0, -1 and 3-D inputs), restated against oracle/qdq.py."""
+    x = torch.randn(4, 8, requires_grad=True)
+    for fn in (Q.round_ste, Q.floor_ste, Q.e4m3_ste):
+        fn(x).sum().backward()
+        assert torch.all(x.grad == 1.0)
+        x.grad = None
+    v = torch.tensor([1.2, 2.7, -0.5], requires_grad=True)
+    y = Q.round_ste(v)
+    assert torch.equal(y, v.round())
+    y.sum().backward()
+    assert torch.equal(v.grad, torch.ones_like(v))
+    t = torch.arange(0, 30, dtype=torch.float32).reshape(3, 10)
+    out, shape, pad = Q.to_groups(t, 4)
+    assert pad == 2 and tuple(out.shape) == (9, 4) and torch.equal(Q.from_groups(out, shape, pad), t)
+    t3 = torch.randn(3, 4, 8)
+    out, shape, pad = Q.to_groups(t3, 0)
+    assert pad == 0 and tuple(out.shape) == (1, t3.numel()) and torch.equal(Q.from_groups(out, shape, pad), t3)
+    t2 = torch.randn(3, 8)
+    out, shape, pad = Q.to_groups(t2, -1)
+    assert pad == 0 and out is t2
+    t4 = torch.randn(2, 3, 10)
+    out, shape, pad = Q.to_groups(t4, 4)
+    assert pad == 2 and torch.equal(Q.from_groups(out, shape, pad), t4)
