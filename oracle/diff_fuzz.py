@@ -1,0 +1,127 @@
+"""Differential fuzz of the oracle against the UNMODIFIED reference, live (build container only: /root/reference).
+
+TEST INFRASTRUCTURE ONLY.  The committed fixtures under tests/golden/ pin the oracle on a fixed set of inputs; this script
+draws fresh random weights / rounding offsets / scales / importance vectors for many seeds and shapes and demands bit-exact
+agreement of values AND autograd gradients between `oracle/qdq.py`, `oracle/pack.py` and the reference's registered
+functions and packers.  Run by tests/test_oracle_vs_reference_live.py in a subprocess (the import shim touches sys.path):
+
+    python -m oracle.diff_fuzz --seeds 8        -> prints one JSON line {"cases": N, "failures": [...]}
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+
+import torch
+
+
+def _same(a, b):
+    if a is None or b is None:
+        return a is None and b is None
+    a, b = a.detach(), b.detach()
+    if a.shape != b.shape:
+        a, b = a.reshape(-1), b.reshape(-1)
+        if a.shape != b.shape:
+            return False
+    nan = torch.isnan(a) & torch.isnan(b)
+    return bool(((a == b) | nan).all())
+
+
+def _weights(n, k, gen, dtype=torch.bfloat16):
+    w = (torch.randn(n, k, generator=gen) * (0.02 + 0.1 * float(torch.rand(1, generator=gen)))).to(dtype)
+    if n > 2:
+        w[0, : min(16, k)] = 0
+        w[1, 0], w[1, 1] = 0.25, -0.25
+        w[2, min(7, k - 1)] = 6.0
+    return w
+
+
+def run(seeds: int):
+    from oracle.ref_shim import import_reference
+
+    import_reference()
+    from auto_round.data_type import QUANT_FUNC_WITH_DTYPE as REF
+    from auto_round.data_type.utils import reshape_pad_tensor_by_group_size
+
+    from oracle import qdq as Q
+
+    failures, cases = [], 0
+    shapes = [(8, 128), (5, 200), (16, 256), (3, 64)]
+    for seed in range(seeds):
+        gen = torch.Generator().manual_seed(1000 + seed)
+        n, k = shapes[seed % len(shapes)]
+        for name, bits, g in (("int_sym", 4, 128), ("int_sym", 2, 32), ("int_sym", 3, 64), ("int_sym", 8, 32), ("int_asym", 2, 32),
+                              ("int_asym", 4, 64), ("mx_fp4", 4, 32), ("nv_fp4", 4, 16)):
+            w = _weights(n, k, gen)
+            grp, _, _ = reshape_pad_tensor_by_group_size(w, g)
+            G = grp.shape[0]
+            v0 = (torch.rand(grp.shape, generator=gen) - 0.5).float()
+            mn0 = (0.4 + 0.6 * torch.rand(G, generator=gen)).float()
+            mx0 = (0.4 + 0.6 * torch.rand(G, generator=gen)).float()
+            gq = torch.randn(w.shape, generator=gen).to(w.dtype)
+            outs = []
+            for which in ("ref", "oracle"):
+                v, mn, mx = (t.clone().requires_grad_(True) for t in (v0, mn0, mx0))
+                if name.startswith("int"):
+                    wmin = torch.clamp(grp.min(1)[0], max=0)
+                    wmax = torch.clamp(grp.max(1)[0], min=0)
+                    if which == "ref":
+                        q, s, z = REF[name](w, bits=bits, group_size=g, v=v, min_scale=mn, max_scale=mx, scale_dtype=torch.float16,
+                                            tensor_min=wmin, tensor_max=wmax, q_scale_thresh=1e-5)
+                    else:
+                        fn = Q.int_sym if name == "int_sym" else Q.int_asym
+                        q, s, z = fn(w, bits, g, v, mn, mx, wmin, wmax, torch.float16, 1e-5)
+                elif name == "mx_fp4":
+                    if which == "ref":
+                        q, s, z = REF["mx_fp4"](w, bits=4, group_size=32, v=v, max_scale=mx, data_type="mx_fp")
+                    else:
+                        q, s, z = Q.mx_fp4(w, 32, v, mx)
+                else:
+                    gs = Q.nv_global_scale(w) * 0.95
+                    if which == "ref":
+                        q, s, z = REF["nv_fp4"](w, bits=4, group_size=16, v=v, global_scale=gs, max_scale=mx)
+                    else:
+                        q, s, z = Q.nv_fp4(w, 16, v, gs, mx)
+                (q.float() * gq.float()).sum().backward()
+                outs.append((q, s, z if isinstance(z, torch.Tensor) else None, v.grad, mx.grad, mn.grad))
+            cases += 1
+            labels = ("qdq", "scale", "zp", "dV", "d max_scale", "d min_scale")
+            for lab, a, b in zip(labels, outs[0], outs[1]):
+                if not _same(a, b):
+                    failures.append(f"seed {seed} {name} w{bits} g{g} [{n}x{k}]: {lab} differs")
+        # RTN variants and the optimized-RTN searches
+        for name, bits, g in (("rtn_int_sym", 4, 128), ("opt_rtn_int_sym", 4, 32), ("opt_rtn_int_sym", 2, 32), ("opt_rtn_int_sym", 3, 128),
+                              ("opt_rtn_nv_fp4", 4, 16), ("opt_rtn_mx_fp4", 4, 32)):
+            w = _weights(n, k, gen)
+            im = (torch.rand(k, generator=gen) ** 2 * 30 + 0.01).float() if seed % 3 else None
+            if im is not None and seed % 5 == 0:
+                im[: max(1, k // 10)] = 0
+            kw = dict(bits=bits, group_size=g)
+            if name == "rtn_int_sym":
+                a = REF[name](w.clone(), **kw)
+                b = Q.rtn_int_sym(w.clone(), bits, g)
+            elif name == "opt_rtn_int_sym":
+                a = REF[name](w.clone(), imatrix=None if im is None else im.clone(), **kw)
+                b = Q.opt_rtn_int_sym(w.clone(), bits, g, im)
+            elif name == "opt_rtn_nv_fp4":
+                gs = Q.nv_global_scale(w) * 0.9
+                a = REF[name](w.clone(), global_scale=gs, **({} if im is None else {"imatrix": im.clone()}), **kw)
+                b = Q.opt_rtn_nv_fp4(w.clone(), 16, gs, 1.0, im)[:3]
+            else:
+                a = REF[name](w.clone(), data_type="mx_fp4", imatrix=None if im is None else im.clone(), **kw)
+                b = Q.opt_rtn_mx_fp4(w.clone(), 32, im)[:3]
+            cases += 1
+            if not _same(a[0], b[0]):
+                failures.append(f"seed {seed} {name} w{bits} g{g} [{n}x{k}] imatrix={'yes' if im is not None else 'no'}: qdq differs")
+            if not _same(a[1].float(), b[1].float()):
+                failures.append(f"seed {seed} {name} w{bits} g{g} [{n}x{k}]: scale differs")
+    return {"cases": cases, "failures": failures}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seeds", type=int, default=8)
+    res = run(ap.parse_args().seeds)
+    print(json.dumps(res))
+    sys.exit(1 if res["failures"] else 0)
