@@ -116,6 +116,60 @@ def run(seeds: int):
                 failures.append(f"seed {seed} {name} w{bits} g{g} [{n}x{k}] imatrix={'yes' if im is not None else 'no'}: qdq differs")
             if not _same(a[1].float(), b[1].float()):
                 failures.append(f"seed {seed} {name} w{bits} g{g} [{n}x{k}]: scale differs")
+    # packers: reference QuantLinear.pack vs oracle/pack.py on fresh qdq weights (every bit of every buffer)
+    import numpy as np
+    import torch.nn as nn
+    from auto_round.export.export_to_autoround.qlinear_fp import QuantLinear as FpQL
+    from auto_round_extension.torch.qlinear_torch import QuantLinear as PlainQL
+    from auto_round_extension.torch.qlinear_torch_zp import QuantLinear as ZpQL
+
+    from oracle import pack as P
+
+    def lin(wq):
+        m = nn.Linear(wq.shape[1], wq.shape[0], bias=False)
+        m.weight.data = wq.clone()
+        return m
+
+    def cmp(tag, got: dict, ref_obj, keys):
+        for key in keys:
+            r = getattr(ref_obj, key)
+            r = r.view(torch.uint8) if r.dtype == torch.float8_e4m3fn else r
+            if not np.array_equal(np.asarray(got[key]), r.numpy()):
+                failures.append(f"{tag}: packed buffer {key} differs")
+
+    for seed in range(seeds):
+        gen = torch.Generator().manual_seed(5000 + seed)
+        for bits, g in ((4, 128), (2, 32), (8, 64), (3, 128)):
+            n, k = 32 * (1 + seed % 2), 256
+            w = _weights(n, k, gen)
+            v = torch.rand(n * k // g, g, generator=gen) - 0.5
+            wq, sc, zp = Q.int_sym(w, bits, g, v)
+            ql = ZpQL(bits, g, k, n, False, g_idx=True)
+            ql.pack(lin(wq.detach()), sc.reshape(n, -1).detach().clone(), int(zp), None, "cpu")
+            cmp(f"seed {seed} pack int_sym w{bits} g{g}", P.pack_int(wq.detach(), sc.reshape(n, -1).detach(), int(zp), bits, g, True), ql,
+                ("qweight", "qzeros", "scales"))
+            cases += 1
+            if bits != 4:
+                wq, sc, zp = Q.int_asym(w, bits, g, v)
+                ql = PlainQL(bits, g, k, n, False)
+                ql.device = "cpu"
+                ql.pack(lin(wq.detach()), sc.reshape(n, -1).detach().clone(), zp.reshape(n, -1).detach().clone(), None, "cpu")
+                cmp(f"seed {seed} pack int_asym w{bits} g{g}",
+                    P.pack_int(wq.detach(), sc.reshape(n, -1).detach(), zp.reshape(n, -1).detach(), bits, g, False), ql,
+                    ("qweight", "qzeros", "scales"))
+                cases += 1
+        n, k = 32, 128
+        w = _weights(n, k, gen)
+        gs = Q.nv_global_scale(w)
+        wq, sc, _ = Q.nv_fp4(w, 16, torch.rand(n * k // 16, 16, generator=gen) - 0.5, gs)
+        ql = FpQL(4, 16, k, n, False, data_type="nv_fp", act_bits=16)
+        ql.pack(lin(wq), sc.reshape(n, -1), global_scale=gs, device="cpu")
+        cmp(f"seed {seed} pack nv_fp4", P.pack_nvfp4(wq, sc.reshape(n, -1), gs), ql, ("weight_packed", "weight_scale"))
+        wq, e, _ = Q.mx_fp4(w, 32, torch.rand(n * k // 32, 32, generator=gen) - 0.5)
+        ql = FpQL(4, 32, k, n, False, data_type="mx_fp", act_bits=16)
+        ql.pack(lin(wq), e.reshape(n, -1), device="cpu")
+        cmp(f"seed {seed} pack mx_fp4", P.pack_mxfp4(wq, e.reshape(n, -1)), ql, ("weight_packed", "weight_scale"))
+        cases += 2
     return {"cases": cases, "failures": failures}
 
 

@@ -18,5 +18,5 @@ def test_oracle_equals_live_reference_on_random_inputs():
     line = [l for l in p.stdout.splitlines() if l.startswith("{")]
     assert line, p.stderr[-2000:]
     res = json.loads(line[-1])
-    assert res["cases"] >= 80
+    assert res["cases"] >= 130
     assert res["failures"] == [], res["failures"][:10]
