@@ -93,9 +93,10 @@ def _oracle(qname, w, bits, g, v, mn, mx, init, gs, grad_fp32=False):
     return Q.nv_fp4(w, g, v, gs, mx, init_scale=1.0 if init is None else init)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
 @pytest.mark.parametrize("name,dt,qname,bits,g,with_init", CASES)
-def test_device_math_on_host_matches_oracle(host_math, name, dt, qname, bits, g, with_init):
-    w, v, mn, mx, init, gs, gq = _inputs(qname, bits, g, with_init, seed=len(name))
+def test_device_math_on_host_matches_oracle(host_math, name, dt, qname, bits, g, with_init, seed):
+    w, v, mn, mx, init, gs, gq = _inputs(qname, bits, g, with_init, seed=100 * seed + len(name))
     is_int = qname.startswith("int")
     vp, mnp, mxp = v.clone().requires_grad_(True), mn.clone().requires_grad_(True), mx.clone().requires_grad_(True)
     out, scale, zp = _oracle(qname, w, bits, g, vp, mnp, mxp, init, gs, grad_fp32=True)
