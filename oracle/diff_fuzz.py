@@ -173,9 +173,55 @@ def run(seeds: int):
     return {"cases": cases, "failures": failures}
 
 
+def run_loops():
+    """Whole tuning runs with NON-default loop options (the committed block fixtures all use the defaults): the reference's
+    AutoRound on the tiny Llama, recorded in memory by oracle/gen_golden.gen_block, replayed by oracle/signround.tune_block."""
+    from oracle.ref_shim import import_reference
+
+    import_reference()
+    import oracle.gen_golden as G
+    from oracle import signround as S
+
+    configs = [
+        ("minmax_off", dict(scheme="W4A16", group_size=32, enable_minmax_tuning=False), S.LayerScheme(4, 32, True, "int"),
+         dict(enable_minmax_tuning=False)),
+        ("last_iter", dict(scheme="W4A16", group_size=32, not_use_best_mse=True), S.LayerScheme(4, 32, True, "int"),
+         dict(not_use_best_mse=True)),
+        ("custom_lr", dict(scheme="W2A16", group_size=32, sym=False, lr=0.01, minmax_lr=0.02), S.LayerScheme(2, 32, False, "int"),
+         dict(lr=0.01, minmax_lr=0.02)),
+        ("nvfp4_bs2", dict(scheme="NVFP4", act_bits=16, act_data_type="float"), S.LayerScheme(4, 16, True, "nv_fp"), dict()),
+    ]
+    failures, cases = [], 0
+    for tag, kw, sc, okw in configs:
+        bs = 2 if tag.endswith("bs2") else 4
+        rec = G.gen_block(tag, kw, iters=5, batch_size=bs, save=False)
+        for bi, b in enumerate(rec["blocks"]):
+            from oracle.tests_support import tiny_block
+            blk = tiny_block(b["block_state"])
+            masks = [(ids != -100).to(torch.long) for ids in b["input_ids"]]
+            res = S.tune_block(blk, b["inputs"], b["others"], b["fp_outputs"], lambda n, m: sc, iters=rec["iters"], batch_size=bs,
+                               token_masks=masks, nv_global_scales=b["nv_gs"] or None, sampler=S.ReplaySampler(b["batches"]), **okw)
+            nvalid = [sum(int(masks[i].sum()) for i in batch) for batch in b["batches"]]
+            got = [l * n for l, n in zip(res.losses, nvalid)]
+            cases += 1
+            if any(abs(a - e) > 1e-6 * abs(e) for a, e in zip(got, b["losses"])) or len(got) != len(b["losses"]):
+                failures.append(f"loop {tag} block {bi}: losses differ")
+            for name, lay in b["layers"].items():
+                if not torch.equal(blk.get_submodule(name).weight.data, lay["weight"]):
+                    failures.append(f"loop {tag} block {bi}: final weight of {name} differs")
+                    break
+    return {"cases": cases, "failures": failures}
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", type=int, default=8)
-    res = run(ap.parse_args().seeds)
+    ap.add_argument("--loops", action="store_true", help="replay whole tuning runs with non-default loop options")
+    args = ap.parse_args()
+    if args.loops:
+        res = run_loops()
+        print(json.dumps(res))
+        sys.exit(1 if res["failures"] else 0)
+    res = run(args.seeds)
     print(json.dumps(res))
     sys.exit(1 if res["failures"] else 0)

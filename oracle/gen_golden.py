@@ -194,7 +194,7 @@ def tiny_mixtral(seed=0):
     return m
 
 
-def gen_block(tag, scheme_kwargs, iters=8, nsamples=8, seqlen=16, batch_size=4, model_factory=None):
+def gen_block(tag, scheme_kwargs, iters=8, nsamples=8, seqlen=16, batch_size=4, model_factory=None, save=True):
     import auto_round.algorithms.quantization.sign_round.quantizer as qz
     import auto_round.compressors.utils as cu
     from auto_round import AutoRound
@@ -263,8 +263,11 @@ def gen_block(tag, scheme_kwargs, iters=8, nsamples=8, seqlen=16, batch_size=4, 
         qz.SignRoundQuantizer.quantize_block = orig_qb
         cu.IndexSampler.next_batch = orig_next
         qz.SignRoundQuantizer._scale_loss_and_backward = orig_bwd
+    if not save:
+        return rec
     torch.save(rec, os.path.join(GOLDEN, f"block_{tag}.pt"))
     print(f"block_{tag}.pt: {len(rec['blocks'])} blocks, losses[0][:3] =", rec["blocks"][0]["losses"][:3])
+    return rec
 
 
 def gen_opt_rtn():
