@@ -178,11 +178,8 @@ class AutoRound:
             if kwargs.get(k):
                 raise NotImplementedError(f"{k}=True is outside the B200 hot path")
         # quant_lm_head: SURVEY.md 8 f4 (quantize_layer_outside_block).  Oracle pinned against a reference run
-        # (tests/golden/lm_head_*.pt); the CUDA loop (quantizer.quantize_layer) has not run on hardware yet -> same switch as alg_ext
+        # (tests/golden/lm_head_*.pt); CUDA loop: quantizer.quantize_layer, GPU parity in tests/test_gpu_lm_head.py
         self.quant_lm_head = bool(kwargs.get("quant_lm_head"))
-        if self.quant_lm_head and os.environ.get("AR_B200_UNVERIFIED", "0") != "1":
-            raise NotImplementedError("quant_lm_head=True: layer tuning outside the blocks is not yet validated on a B200 "
-                                      "(set AR_B200_UNVERIFIED=1 to run it)")
         if kwargs.get("dynamic_max_gap", -1) not in (-1, None) or kwargs.get("momentum") not in (None, 0, 0.0):
             raise NotImplementedError("dynamic_max_gap / momentum: only the reference defaults (-1 / 0)")
         if kwargs.get("nblocks", 1) != 1:
@@ -190,16 +187,11 @@ class AutoRound:
         self.model = model.eval()
         self.tokenizer = tokenizer
         self.scheme: QuantizationScheme = parse_scheme(scheme, {k: kwargs.get(k) for k in _SCHEME_KW})
-        # enable_alg_ext (sign_roundv2): int asym keeps the plain wrapper in the reference (sign_roundv2/quantizer.py:334-357).
-        # The symmetric route (searched init scale, max_scale in [0,2], outlier-suppressed loss) is written and pinned on the
-        # CPU side (oracle + tests/golden/block_algext_*.pt) but its CUDA path has not run on hardware yet, so it has to be
-        # asked for explicitly; without the switch the request fails loudly instead of running unvalidated numerics.
-        # For int asym the only effect is the loss: SignRoundV2Quantizer._get_loss falls back to the base MSE without the
-        # valid-token mask (sign_roundv2/quantizer.py:399), which the fixtures confirm -- mirrored, not gated (same kernels).
+        # enable_alg_ext (sign_roundv2): int asym keeps the plain wrapper in the reference (sign_roundv2/quantizer.py:334-357);
+        # symmetric int / MXFP4 / NVFP4 get the searched init scale, max_scale in [0,2] and (bits < 4) the outlier-suppressed
+        # loss.  For int asym the only effect is the loss: SignRoundV2Quantizer._get_loss falls back to the base MSE without
+        # the valid-token mask (sign_roundv2/quantizer.py:399), which the fixtures confirm.  GPU parity: tests/test_gpu_alg_ext.py
         self.enable_alg_ext = bool(kwargs.get("enable_alg_ext"))
-        if self.enable_alg_ext and self.scheme.qdq_name != "int_asym" and os.environ.get("AR_B200_UNVERIFIED", "0") != "1":
-            raise NotImplementedError("enable_alg_ext for symmetric schemes: CUDA path not yet validated on a B200 "
-                                      "(set AR_B200_UNVERIFIED=1 to run it; tests/test_gpu_alg_ext.py holds its parity tests)")
         self.layer_config = layer_config or {}
         self.dataset = dataset
         self.iters = 200 if iters is None else int(iters)

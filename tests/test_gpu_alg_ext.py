@@ -1,9 +1,7 @@
 """enable_alg_ext on the GPU: searched init scale, max_scale in [0, 2], outlier-suppressed loss.
 
-STATUS: written when round 1's GPU budget was almost spent -- the CPU side (oracle + the four reference fixtures
-tests/golden/block_algext_*.pt, tests/test_oracle_golden.py) is pinned bit-exact and the kernels passed the torch-free
-tools/gpu_selftest on the B200 (profiles/r01_gpu_selftest.txt), but this file (and the loop it drives) has NOT run yet.  The tests therefore only run when AR_B200_UNVERIFIED=1 (the same switch the product path asks for);
-the first GPU session of the next round runs them with the switch, fixes what they find and removes the gate.
+First run on a B200 in round 2 (gpurun_out/r2_gated_all.log -> profiles/r02_gated_modules.txt): all green once the
+all-zero-group NaN of the reference's autograd is masked in the comparison.
 
 What they state (same bars as tests/test_gpu_kernels.py / test_gpu_engine.py):
   * fake-quant forward with an init scale: bit-exact to the oracle (int sym, MXFP4, NVFP4)
@@ -22,8 +20,6 @@ pytestmark = pytest.mark.gpu
 
 if not torch.cuda.is_available():
     pytest.skip("CUDA device required", allow_module_level=True)
-if os.environ.get("AR_B200_UNVERIFIED", "0") != "1":
-    pytest.skip("enable_alg_ext CUDA path not yet validated on hardware (set AR_B200_UNVERIFIED=1)", allow_module_level=True)
 
 from auto_round_b200 import ops  # noqa: E402
 from auto_round_b200.quantizer import SignRoundQuantizer  # noqa: E402
@@ -95,8 +91,12 @@ def test_init_scale_backward(name):
     ref_dv = vp.grad.reshape(n, k)
     assert torch.allclose(dv.cpu(), ref_dv, rtol=2e-5, atol=1e-9), name
     ref_dm = mp.grad
-    denom = ref_dm.abs().max().clamp_min(1e-12)
-    assert float((dmax.cpu() - ref_dm).abs().max() / denom) <= 2e-3, name
+    # row 0's first group is all-zero: the reference's autograd yields NaN there for mx/nv (0 * inf), the CUDA path defines
+    # d(max_scale) = 0 -- compare the finite positions, require 0 at the NaN ones
+    nan = torch.isnan(ref_dm)
+    assert int(nan.sum()) <= 1 and float(dmax.cpu()[nan].abs().sum()) == 0.0, name
+    denom = ref_dm[~nan].abs().max().clamp_min(1e-12)
+    assert float((dmax.cpu() - ref_dm)[~nan].abs().max() / denom) <= 2e-3, name
     if dmin is not None:
         assert float(dmin.abs().max()) == 0.0
 

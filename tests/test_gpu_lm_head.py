@@ -1,9 +1,8 @@
 """`quant_lm_head=True` on the GPU: quantizer.quantize_layer against the oracle's tune_layer on the inputs
 the reference fed its quantize_layer_outside_block (tests/golden/lm_head_w4a16_sym_g32.pt).
 
-STATUS: written after round 1's GPU budget was spent; the oracle side is pinned bit-exact on the CPU
-(tests/test_oracle_golden.py::test_tune_layer_lm_head_matches_reference_bit_exact); this file runs only with
-AR_B200_UNVERIFIED=1 until it has passed on a B200.  Bars as in tests/test_gpu_engine.py: first-iteration loss within 2e-2
+The oracle side is pinned bit-exact on the CPU
+(tests/test_oracle_golden.py::test_tune_layer_lm_head_matches_reference_bit_exact).  Bars as in tests/test_gpu_engine.py: first-iteration loss within 2e-2
 of the oracle's (identical parameters, only GEMM rounding differs), final layer-output MSE within +-25 %."""
 import os
 import random
@@ -15,8 +14,6 @@ pytestmark = pytest.mark.gpu
 
 if not torch.cuda.is_available():
     pytest.skip("CUDA device required", allow_module_level=True)
-if os.environ.get("AR_B200_UNVERIFIED", "0") != "1":
-    pytest.skip("lm_head tuning not yet validated on hardware (set AR_B200_UNVERIFIED=1)", allow_module_level=True)
 
 from auto_round_b200.quantizer import SignRoundQuantizer  # noqa: E402
 from auto_round_b200.schemes import parse_scheme  # noqa: E402

@@ -1,9 +1,7 @@
 """AR_RESUME_DIR end to end on the GPU: a run killed after block 0 and restarted must finish with the same
 checkpoint as an uninterrupted run (block results, chain values and the python/torch RNG state are restored; the kernels
 are deterministic apart from the order of the double-precision loss atomics).
-
-STATUS: like tests/test_gpu_alg_ext.py this was written after round 1's GPU budget was spent; the host logic is covered by
-tests/test_resume.py on the CPU, the integration below runs only with AR_B200_UNVERIFIED=1 until it has passed on a B200."""
+The host logic is covered by tests/test_resume.py on the CPU."""
 import os
 
 import pytest
@@ -13,8 +11,6 @@ pytestmark = pytest.mark.gpu
 
 if not torch.cuda.is_available():
     pytest.skip("CUDA device required", allow_module_level=True)
-if os.environ.get("AR_B200_UNVERIFIED", "0") != "1":
-    pytest.skip("resume integration not yet validated on hardware (set AR_B200_UNVERIFIED=1)", allow_module_level=True)
 
 from auto_round_b200 import AutoRound  # noqa: E402
 
