@@ -37,6 +37,7 @@ SIGNATURES = {
     "ar_fq_linear_fwd": [_QS, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "ar_fq_linear_bwd_dx": [_QS, _P, _L, _P, _P, _P],
     "ar_fq_linear_bwd_dw": [_QS, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
+    "ar_fq_update": [_QS, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _F, _P, _P, _P, _P, _P, _P],
     "ar_mse_fwd_bwd": [_P, _P, _P, _L, _L, _F, _F, _P, _P, _P],
     "ar_best_update": [_P, _D, _D, _I, _P, _P, _P, _P, _P, _P],
     "ar_signsgd_step": [_P, _P, _I, _P, _P, _P, _P, _I, _P, _L, _L, _F, _P],
@@ -59,7 +60,8 @@ SIGNATURES = {
     "ar_imatrix_accum": [_P, _L, _I, _P, _P],
     "ar_absdiff_hist": [_P, _P, _L, _P, _P],
     "ar_topk_threshold": [_P, _L, _P, _P],
-    "ar_mse_outlier_fwd_bwd": [_P, _P, _P, _L, _L, _F, _P, _P, _P, _P],
+    "ar_topk_threshold_ranks": [_P, _I, _I, _P, _L, _P, _P],
+    "ar_mse_outlier_fwd_bwd": [_P, _P, _P, _L, _L, _L, _F, _P, _P, _P, _P],
 }
 
 _lib = None

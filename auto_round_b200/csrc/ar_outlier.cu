@@ -52,14 +52,24 @@ __global__ void __launch_bounds__(1024) absdiff_hist_kernel(const U4* __restrict
 
 // pass 2: sel[0] = threshold pattern t with count(> t) < k <= count(>= t); sel[1] = k - count(> t) ("need": how many
 // elements AT t are dropped); sel[2] = 0 (tie counter of pass 3).  Clears the histogram for the next iteration.
-__global__ void __launch_bounds__(1024) topk_threshold_kernel(uint32_t* __restrict__ hist, unsigned long long k,
+// Data parallel: `hist` holds `world` per-rank histograms [world, 32768] (all-gathered); the threshold comes from their sum
+// (the top-k is global over the batch) and the `need` ties at the threshold are handed out in rank order, so that exactly
+// k elements are dropped over all ranks: need_r = clamp(need - sum_{r' < r} ties_r', 0, ties_r).  `clear` (this rank's own
+// histogram) is re-armed.
+__global__ void __launch_bounds__(1024) topk_threshold_kernel(const uint32_t* __restrict__ hist, int world, int rank,
+                                                              uint32_t* __restrict__ clear, unsigned long long k,
                                                               uint32_t* __restrict__ sel) {
   __shared__ unsigned long long part[1024];
   const int t = threadIdx.x;                       // thread t owns bins [32 t, 32 t + 32)
   unsigned long long s = 0;
   uint32_t c[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) { c[i] = hist[t * 32 + i]; s += c[i]; }
+  for (int i = 0; i < 32; ++i) {
+    uint32_t v = 0;
+    for (int r = 0; r < world; ++r) v += hist[(size_t)r * kBins + t * 32 + i];
+    c[i] = v;
+    s += v;
+  }
   part[t] = s;
   __syncthreads();
   // inclusive suffix sum over the 1024 partials (Hillis-Steele, 10 steps)
@@ -74,8 +84,14 @@ __global__ void __launch_bounds__(1024) topk_threshold_kernel(uint32_t* __restri
     unsigned long long cum = above;
     for (int i = 31; i >= 0; --i) {
       if (cum + c[i] >= k) {
+        unsigned long long need = k - cum;         // ties to drop over all ranks
+        for (int r = 0; r < rank; ++r) {
+          const unsigned long long mine = hist[(size_t)r * kBins + t * 32 + i];
+          need = need > mine ? need - mine : 0ull;
+        }
+        const unsigned long long own = hist[(size_t)rank * kBins + t * 32 + i];
         sel[0] = (uint32_t)(t * 32 + i);
-        sel[1] = (uint32_t)(k - cum);
+        sel[1] = (uint32_t)(need < own ? need : own);
         break;
       }
       cum += c[i];
@@ -85,8 +101,9 @@ __global__ void __launch_bounds__(1024) topk_threshold_kernel(uint32_t* __restri
     sel[2] = 0u;
     if (part[0] < k) { sel[0] = 0u; sel[1] = 0xffffffffu; }    // fewer than k elements in total: drop everything
   }
+  __syncthreads();                                 // (world == 1: `clear` aliases `hist`; every read above is done)
 #pragma unroll
-  for (int i = 0; i < 32; ++i) hist[t * 32 + i] = 0u;
+  for (int i = 0; i < 32; ++i) clear[t * 32 + i] = 0u;
 }
 
 // pass 3: loss_sum += sum((|d| m keep)^2) (double, unnormalised); dpred = bf16 of autograd's chain
@@ -162,13 +179,23 @@ extern "C" int ar_absdiff_hist(const void* pred, const void* ref, int64_t numel,
 
 extern "C" int ar_topk_threshold(uint32_t* hist, int64_t k, uint32_t* sel, void* stream) {
   AR_REQUIRE(hist && sel && k >= 1, AR_E_BADARG, "ar_topk_threshold: bad arguments");
-  topk_threshold_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(hist, (unsigned long long)k, sel);
+  topk_threshold_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(hist, 1, 0, hist, (unsigned long long)k, sel);
+  AR_CHECK_LAUNCH();
+  return AR_OK;
+}
+
+extern "C" int ar_topk_threshold_ranks(const uint32_t* hist_all, int world, int rank, uint32_t* hist_local, int64_t k,
+                                       uint32_t* sel, void* stream) {
+  AR_REQUIRE(hist_all && hist_local && sel && k >= 1 && world >= 1 && rank >= 0 && rank < world, AR_E_BADARG,
+             "ar_topk_threshold_ranks: bad arguments");
+  topk_threshold_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(hist_all, world, rank, hist_local, (unsigned long long)k, sel);
   AR_CHECK_LAUNCH();
   return AR_OK;
 }
 
 extern "C" int ar_mse_outlier_fwd_bwd(const void* pred, const void* ref, const uint8_t* row_mask, int64_t rows, int64_t cols,
-                                      float upstream, uint32_t* sel, double* loss_sum, void* dpred, void* stream) {
+                                      int64_t numel_total, float upstream, uint32_t* sel, double* loss_sum, void* dpred,
+                                      void* stream) {
   AR_REQUIRE(pred && ref && sel && loss_sum && rows > 0 && cols > 0, AR_E_BADARG, "ar_mse_outlier_fwd_bwd: bad arguments");
   AR_REQUIRE(cols % 8 == 0, AR_E_UNSUPPORTED, "ar_mse_outlier_fwd_bwd: cols must be a multiple of 8");
   const int64_t total = rows * (cols / 8);
@@ -176,7 +203,8 @@ extern "C" int ar_mse_outlier_fwd_bwd(const void* pred, const void* ref, const u
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  const float up_over_n = upstream / (float)(rows * cols);        // mean backward: grad_output / numel
+  // mean backward: grad_output / numel; numel_total > 0: the mean runs over the GLOBAL batch of a data-parallel iteration
+  const float up_over_n = upstream / (float)(numel_total > 0 ? numel_total : rows * cols);
   mse_outlier_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)pred, (const uint16_t*)ref, row_mask, rows,
                                                                          (int)(cols / 8), up_over_n, sel, loss_sum,
                                                                          (uint16_t*)dpred);

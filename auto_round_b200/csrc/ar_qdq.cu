@@ -285,6 +285,128 @@ static void launch_bwd_g(int g, dim3 grid, cudaStream_t st, const QArgs& a, cons
   }
 }
 
+// ------------------------------------------------------------------------------------ fused per-layer update
+// One pass over a layer's weights per sign-SGD iteration (replaces: fused grad-w epilogue -> sign-SGD kernel -> next
+// iteration's qdq forward, 30-34 B/weight in three launches):
+//   Gq = dL/dWq (bf16, the plain grad-w GEMM's output; under data parallelism the reduce-scattered SUM over ranks)
+//   fake-quant backward in registers (dV = Gq*s*mask, group sums -> d min/max_scale)            wrapper.py:273-290 autograd
+//   best-param snapshot of the PRE-update parameters when *flag                                   quantizer.py:511-515
+//   p <- p - lr_t * sign(grad), min/max_scale clamped to [0, clamp_hi]                            sign_sgd.py:369-389
+//   Wq' = qdq(W; V', scales') for the NEXT iteration's forward / grad-in GEMMs                    wrapper.py:244-293
+// Algorithmic bytes / weight: read 2 (W) + 4 (V) + 2 (Gq), write 4 (V') + 2 (Wq') = 14 B (+4 B when the snapshot fires).
+// Rows [row0, row1) only: a data-parallel rank owns a row shard; `gq` is indexed from row `gq_row0`.
+struct UpdArgs {
+  const uint16_t* gq;      // bf16 [rows, K]
+  int gq_row0, row0, row1;
+  float* v;                // in/out [N, kpad]
+  float* mn;               // in/out [G] or null
+  float* mx;               // in/out [G]
+  float* best_v;           // snapshot targets (null: no snapshot)
+  float* best_mn;
+  float* best_mx;
+  const int32_t* flag;
+  const float* lr_table;
+  int iter;
+  const int32_t* it_ptr;
+  float clamp_hi;
+  uint16_t* wq;            // out bf16 [N, K]
+  float* dv_dbg;           // optional pre-sign gradients (tests): [N, kpad], [G], [G]
+  float* dmn_dbg;
+  float* dmx_dbg;
+  const int32_t* has_grad; // optional: *has_grad == 0 -> the layer received no gradient this iteration: leave it untouched
+};
+
+__device__ __forceinline__ float sgnf(float g) { return (g > 0.f) ? 1.f : ((g < 0.f) ? -1.f : 0.f); }
+
+template <class Ctx, int G, bool IS_FP4>
+__global__ void __launch_bounds__(kThreads) fq_update_kernel(QArgs a, UpdArgs u) {
+  constexpr int LPG = G / 8;
+  if (u.has_grad != nullptr && *u.has_grad == 0) return;
+  const int cpr = a.kpad / 8;
+  const int64_t total = (int64_t)(u.row1 - u.row0) * cpr;
+  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const bool valid = c < total;
+  const int64_t cc = valid ? c : 0;
+  const int n = u.row0 + (int)(cc / cpr);
+  const int k0 = (int)(cc % cpr) * 8;
+  const int64_t gidx = (int64_t)n * (a.kpad / G) + k0 / G;
+  const bool vec = (a.k % 8) == 0;
+  const int iter = u.it_ptr ? *u.it_ptr : u.iter;
+  const float lr_v = u.lr_table[2 * iter], lr_s = u.lr_table[2 * iter + 1];
+  const bool snap = (u.flag != nullptr) && (*u.flag != 0) && (u.best_v != nullptr);
+  float w[8], v[8], g[8];
+  load_w8(a.w, (int64_t)n * a.k, k0, a.k, vec, w);
+  load_w8(u.gq, (int64_t)(n - u.gq_row0) * a.k, k0, a.k, vec, g);
+  const int64_t voff = (int64_t)n * a.kpad + k0;
+  load_f8(u.v, voff, v);
+  a.v = u.v; a.mn = u.mn; a.mx = u.mx;
+  Ctx ctx;
+  GroupIn gi;
+  make_group<Ctx, G, IS_FP4>(a, gidx, w, valid, ctx, gi);
+  GroupAcc acc;
+  float d[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ctx.bwd(w[i], v[i], g[i], d[i], acc);
+  acc.a = group_sum<LPG>(acc.a);
+  acc.b = group_sum<LPG>(acc.b);
+  if (!valid) return;
+  float gmn, gmx;
+  ctx.finish(acc, gi, gmn, gmx);
+  const bool lead = (k0 % G) == 0;
+  if (u.dv_dbg) {
+    *reinterpret_cast<float4*>(u.dv_dbg + voff) = make_float4(d[0], d[1], d[2], d[3]);
+    *reinterpret_cast<float4*>(u.dv_dbg + voff + 4) = make_float4(d[4], d[5], d[6], d[7]);
+    if (lead && u.dmx_dbg) u.dmx_dbg[gidx] = gmx;
+    if (lead && u.dmn_dbg) u.dmn_dbg[gidx] = gmn;
+  }
+  if (snap) {
+    *reinterpret_cast<float4*>(u.best_v + voff) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(u.best_v + voff + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    if (lead) {
+      if (u.best_mx) u.best_mx[gidx] = gi.mx;
+      if (u.best_mn && u.mn) u.best_mn[gidx] = gi.mn;
+    }
+  }
+  // sign-SGD step (every lane of a group derives the same new scales from the shuffled group sums)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = v[i] - lr_v * sgnf(d[i]);
+  *reinterpret_cast<float4*>(u.v + voff) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(u.v + voff + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  gi.mx = clampf(gi.mx - lr_s * sgnf(gmx), 0.f, u.clamp_hi);
+  if (u.mn) gi.mn = clampf(gi.mn - lr_s * sgnf(gmn), 0.f, u.clamp_hi);
+  if (lead) {
+    u.mx[gidx] = gi.mx;
+    if (u.mn) u.mn[gidx] = gi.mn;
+  }
+  // next iteration's fake-quant weight
+  ctx.setup(gi);
+  uint32_t packed[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t lo = f32_to_bf16_bits(ctx.fwd(w[2 * i], v[2 * i]));
+    const uint32_t hi = f32_to_bf16_bits(ctx.fwd(w[2 * i + 1], v[2 * i + 1]));
+    packed[i] = lo | (hi << 16);
+  }
+  if (vec && k0 + 8 <= a.k) {
+    *reinterpret_cast<U4*>(u.wq + (int64_t)n * a.k + k0) = U4{packed[0], packed[1], packed[2], packed[3]};
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (k0 + i < a.k) u.wq[(int64_t)n * a.k + k0 + i] = (uint16_t)((packed[i / 2] >> (16 * (i & 1))) & 0xffffu);
+  }
+}
+
+template <class Ctx, bool FP4>
+static void launch_upd_g(int g, dim3 grid, cudaStream_t st, const QArgs& a, const UpdArgs& u) {
+  switch (g) {
+    case 16: fq_update_kernel<Ctx, 16, FP4><<<grid, kThreads, 0, st>>>(a, u); break;
+    case 32: fq_update_kernel<Ctx, 32, FP4><<<grid, kThreads, 0, st>>>(a, u); break;
+    case 64: fq_update_kernel<Ctx, 64, FP4><<<grid, kThreads, 0, st>>>(a, u); break;
+    case 128: fq_update_kernel<Ctx, 128, FP4><<<grid, kThreads, 0, st>>>(a, u); break;
+    default: fq_update_kernel<Ctx, 256, FP4><<<grid, kThreads, 0, st>>>(a, u); break;
+  }
+}
+
 }  // namespace ar
 
 using namespace ar;
@@ -368,6 +490,36 @@ extern "C" int ar_absmax(const void* w, int64_t numel, float* amax, void* stream
 extern "C" int ar_nv_global_scale(const float* amax, float* gs, void* stream) {
   AR_REQUIRE(amax && gs, AR_E_BADARG, "bad args");
   nv_gscale_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(amax, gs);
+  AR_CHECK_LAUNCH();
+  return AR_OK;
+}
+
+extern "C" int ar_fq_update(const ar_qspec* q, const void* w, float* v, float* mn, float* mx, const void* wmin,
+                            const void* wmax, const float* gscale, const void* gq, int gq_row0, int row0, int row1,
+                            float* best_v, float* best_mn, float* best_mx, const int32_t* flag, const float* lr_table,
+                            int iter, const int32_t* it_ptr, float clamp_hi, void* wq_out, float* dv_dbg, float* dmn_dbg,
+                            float* dmx_dbg, const int32_t* has_grad, void* stream) {
+  if (int rc = check_spec(q)) return rc;
+  AR_REQUIRE(w && v && mx && gq && lr_table && wq_out, AR_E_BADARG, "w/v/max_scale/gq/lr_table/wq must be non-null");
+  AR_REQUIRE((wmin == nullptr) == (wmax == nullptr), AR_E_BADARG, "wmin/wmax must both be given or both null");
+  AR_REQUIRE(q->dtype != AR_DT_NV_FP4 || gscale != nullptr, AR_E_BADARG, "nv_fp4 needs gscale");
+  AR_REQUIRE(0 <= row0 && row0 <= row1 && row1 <= q->n && gq_row0 <= row0 && iter >= 0, AR_E_BADARG,
+             "bad row range [%d,%d) of %d (gq from row %d)", row0, row1, q->n, gq_row0);
+  if (row0 == row1) return AR_OK;
+  const QArgs a = make_args(q, w, v, mn, mx, wmin, wmax, gscale);
+  UpdArgs u;
+  u.gq = (const uint16_t*)gq; u.gq_row0 = gq_row0; u.row0 = row0; u.row1 = row1;
+  u.v = v; u.mn = mn; u.mx = mx; u.best_v = best_v; u.best_mn = best_mn; u.best_mx = best_mx; u.flag = flag;
+  u.lr_table = lr_table; u.iter = iter; u.it_ptr = it_ptr; u.clamp_hi = clamp_hi; u.wq = (uint16_t*)wq_out;
+  u.dv_dbg = dv_dbg; u.dmn_dbg = dmn_dbg; u.dmx_dbg = dmx_dbg; u.has_grad = has_grad;
+  const int64_t chunks = (int64_t)(row1 - row0) * (a.kpad / 8);
+  const dim3 grid((unsigned)((chunks + kThreads - 1) / kThreads));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = q->group_size;
+  if (q->dtype == AR_DT_INT_SYM) launch_upd_g<IntSym, false>(g, grid, st, a, u);
+  else if (q->dtype == AR_DT_INT_ASYM) launch_upd_g<IntAsym, false>(g, grid, st, a, u);
+  else if (q->dtype == AR_DT_MX_FP4) launch_upd_g<MxFp4, true>(g, grid, st, a, u);
+  else launch_upd_g<NvFp4, true>(g, grid, st, a, u);
   AR_CHECK_LAUNCH();
   return AR_OK;
 }

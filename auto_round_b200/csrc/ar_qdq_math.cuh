@@ -34,10 +34,24 @@ struct GroupAcc {
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
+// w / s without the IEEE division sequence on the hot path: with rs = RN(1/s) (one real division per GROUP),
+//   q0 = RN(w*rs);  e = w - s*q0 (exact, FMA);  q = RN(q0 + e*rs)
+// is the correctly rounded quotient (Markstein) whenever nothing under/overflows.  For the operands that occur here --
+// w a bf16 weight, s an fp16-valued scale with |s| >= 1e-5 -- tests/test_div_exact.py checks ALL 3.2e9 pairs bit-for-bit
+// against w / s; zero, denormal-range and huge numerators take the real division (and keep the sign of zero).
+__device__ __forceinline__ float div_exact(float w, float s, float rs) {
+  const float aw = fabsf(w);
+  if (!(aw > 1e-30f && aw < 1e30f)) return w / s;
+  const float q0 = w * rs;
+  const float e = __fmaf_rn(-q0, s, w);
+  return __fmaf_rn(e, rs, q0);
+}
+
 // ------------------------------------------------------------------------------------------------ int_sym
 struct IntSym {
   float kMaxq;    // 2^(bits-1)
   float s;        // scale: fp16-rounded, threshold-clipped, as fp32
+  float rs;       // RN(1/s), see div_exact
   float route_mx; // d s_raw / d max_scale
   float route_mn; // d s_raw / d min_scale
 
@@ -51,6 +65,7 @@ struct IntSym {
       else             { s = fmaxf(s_raw, thr);  pass = (s_raw >= thr); }
       route_mx = pass ? g.init : 0.f;
       route_mn = 0.f;                                  // min_scale does not enter this graph
+      rs = 1.f / s;
       return;
     }
     const float lo = -(g.wmin * g.mn);
@@ -66,19 +81,20 @@ struct IntSym {
     const float base = pass ? (sgn / kMaxq) : 0.f;
     route_mx = base * whi * g.wmax;
     route_mn = base * (1.f - whi) * (-g.wmin);
+    rs = 1.f / s;
   }
   __device__ __forceinline__ float code(float w, float v) const {   // q in [-maxq, maxq-1]
-    return clampf(rintf(w / s + v), -kMaxq, kMaxq - 1.f);
+    return clampf(rintf(div_exact(w, s, rs) + v), -kMaxq, kMaxq - 1.f);
   }
   __device__ __forceinline__ float fwd(float w, float v) const { return s * code(w, v); }
   __device__ __forceinline__ void bwd(float w, float v, float gq, float& dv, GroupAcc& acc) const {
-    const float ws = w / s;
+    const float ws = div_exact(w, s, rs);
     const float r = rintf(ws + v);
     const bool in = (r >= -kMaxq) && (r <= kMaxq - 1.f);
     const float q = clampf(r, -kMaxq, kMaxq - 1.f);
     const float dt = in ? gq * s : 0.f;
     dv = dt;
-    acc.a += gq * q - dt * (ws / s);                                 // d L / d s
+    acc.a += gq * q - dt * div_exact(ws, s, rs);                     // d L / d s  (only its sign is used downstream)
   }
   __device__ __forceinline__ void finish(const GroupAcc& acc, const GroupIn&, float& dmin, float& dmax) const {
     dmax = acc.a * route_mx;
@@ -91,7 +107,7 @@ struct IntSym {
 // ----------------------------------------------------------------------------------------------- int_asym
 struct IntAsym {
   float kMaxq;    // 2^bits - 1
-  float s, zp, lo;
+  float s, rs, zp, lo;
   bool pass;
 
   __device__ __forceinline__ void init(int bits) { kMaxq = (float)((1 << bits) - 1); }
@@ -102,21 +118,22 @@ struct IntAsym {
     const float thr = f16_round(g.thr);
     s = fmaxf(s_raw, thr);
     pass = (s_raw >= thr);
+    rs = 1.f / s;
     zp = rintf((-lo) / s);
   }
   __device__ __forceinline__ float code(float w, float v) const {   // q in [0, maxq]
-    return clampf(rintf(w / s + v) + zp, 0.f, kMaxq);
+    return clampf(rintf(div_exact(w, s, rs) + v) + zp, 0.f, kMaxq);
   }
   __device__ __forceinline__ float fwd(float w, float v) const { return s * (code(w, v) - zp); }
   __device__ __forceinline__ void bwd(float w, float v, float gq, float& dv, GroupAcc& acc) const {
-    const float ws = w / s;
+    const float ws = div_exact(w, s, rs);
     const float u = rintf(ws + v) + zp;
     const bool in = (u >= 0.f) && (u <= kMaxq);
     const float q = clampf(u, 0.f, kMaxq);
     const float gs = gq * s;
     const float dt = in ? gs : 0.f;
     dv = dt;
-    acc.a += gq * (q - zp) - dt * (ws / s);                          // d L / d s  (direct + through W/s)
+    acc.a += gq * (q - zp) - dt * div_exact(ws, s, rs);              // d L / d s  (direct + through W/s)
     acc.b += dt - gs;                                                // d L / d zp (clamped elements only)
   }
   __device__ __forceinline__ void finish(const GroupAcc& acc, const GroupIn& g, float& dmin, float& dmax) const {
@@ -155,6 +172,7 @@ __device__ __forceinline__ float mx_quant_element(float t) {
 struct MxFp4 {
   __device__ __forceinline__ void init(int) {}
   float s;      // 2^e
+  float rs;     // 2^-e: w / s == w * rs exactly (power of two)
   float e;      // shared exponent (after -emax and clamp)
   float m;      // amax * max_scale
   bool pass;
@@ -166,13 +184,14 @@ struct MxFp4 {
     e = clampf(ef, -127.f, 127.f);
     pass = (ef >= -127.f) && (ef <= 127.f) && (m != 0.f);
     s = ldexpf(1.f, (int)e);
+    rs = ldexpf(1.f, -(int)e);
   }
   __device__ __forceinline__ float fwd(float w, float v) const {
-    const float t = clampf(w / s + v, -6.f, 6.f);
+    const float t = clampf(w * rs + v, -6.f, 6.f);
     return mx_quant_element(t) * s;
   }
   __device__ __forceinline__ void bwd(float w, float v, float gq, float& dv, GroupAcc& acc) const {
-    const float ws = w / s;
+    const float ws = w * rs;
     const float t = ws + v;
     const bool in = (t >= -6.f) && (t <= 6.f);
     const float tc = clampf(t, -6.f, 6.f);
@@ -181,7 +200,7 @@ struct MxFp4 {
     const float f = (fabsf(tc) >= 1.f) ? (o / tc) : (tc != 0.f ? 1.f : 0.f);
     const float dt = in ? gq * s * f : 0.f;
     dv = dt;
-    acc.a += gq * o - dt * (ws / s);                                  // d L / d s
+    acc.a += gq * o - dt * (ws * rs);                                 // d L / d s
   }
   __device__ __forceinline__ void finish(const GroupAcc& acc, const GroupIn& g, float& dmin, float& dmax) const {
     // s = 2^e, e = floor_ste(log2 m) - 2  =>  ds/dm = s / m ;  m = amax * max_scale

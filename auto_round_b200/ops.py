@@ -206,6 +206,27 @@ def fq_linear_bwd_dw(spec: Spec, dy2d, x2d, w, v, min_scale, max_scale, wmin, wm
            "ar_fq_linear_bwd_dw")
 
 
+def fq_update(spec: Spec, w, v, min_scale, max_scale, wmin, wmax, gscale, gq, wq_out, lr_table, best_v=None, best_min=None,
+              best_max=None, flag=None, it=0, it_dev=None, clamp_hi=1.0, row0=0, row1=None, gq_row0=0, init_scale=None,
+              dbg=None, has_grad=None):
+    """Fused per-layer update (include/ar_b200.h ar_fq_update): qdq backward from the bf16 dWq `gq`, snapshot, sign-SGD
+    step, next iteration's fake-quant weight into `wq_out` -- rows [row0, row1).  `dbg` = (dv, dmin, dmax) fp32 outputs."""
+    _want(w, torch.bfloat16, "w")
+    _want(gq, torch.bfloat16, "gq")
+    _want(wq_out, torch.bfloat16, "wq_out")
+    for t, nm in ((v, "v"), (min_scale, "min_scale"), (max_scale, "max_scale"), (best_v, "best_v"), (lr_table, "lr_table")):
+        _want(t, torch.float32, nm)
+    row1 = spec.n if row1 is None else row1
+    if gq.numel() < (row1 - gq_row0) * spec.k:
+        raise ValueError("gq does not cover rows [gq_row0, row1)")
+    cs = _cspec(spec, init_scale)
+    dv, dmn, dmx = dbg if dbg is not None else (None, None, None)
+    _check(_lib.load().ar_fq_update(C.byref(cs), _p(w), _p(v), _p(min_scale), _p(max_scale), _p(wmin), _p(wmax), _p(gscale),
+                                    _p(gq), int(gq_row0), int(row0), int(row1), _p(best_v), _p(best_min), _p(best_max),
+                                    _p(flag), _p(lr_table), int(it), _p(it_dev), float(clamp_hi), _p(wq_out), _p(dv), _p(dmn),
+                                    _p(dmx), _p(has_grad), _stream()), "ar_fq_update")
+
+
 def mse_fwd_bwd(pred2d, ref2d, row_mask, inv_numel, upstream, loss_sum, dpred=None, want_grad=True):
     """loss_sum (double [1]) += sum(((pred-ref)*m)^2); returns dpred bf16 (see include/ar_b200.h)."""
     _want(pred2d, torch.bfloat16, "pred")
@@ -456,11 +477,15 @@ class OutlierSelect:
     def __init__(self, device):
         self.hist = torch.zeros(32768, dtype=torch.int32, device=device)
         self.sel = torch.zeros(4, dtype=torch.int32, device=device)
+        self.hist_all = None                  # [world, 32768] under data parallelism
 
 
-def mse_outlier_fwd_bwd(pred2d, ref2d, row_mask, upstream, loss_sum, scratch: OutlierSelect, dpred=None, want_grad=True):
+def mse_outlier_fwd_bwd(pred2d, ref2d, row_mask, upstream, loss_sum, scratch: OutlierSelect, dpred=None, want_grad=True,
+                        numel_global=None, all_gather=None, rank=0, world=1):
     """SignRoundV2Quantizer._get_loss with its backward: drops the numel // 1000 largest |pred - ref| (selection on the
-    bf16 difference, token mask ignored there), loss_sum (double [1]) += sum((|d| * mask * keep)^2); returns dpred bf16."""
+    bf16 difference, token mask ignored there), loss_sum (double [1]) += sum((|d| * mask * keep)^2); returns dpred bf16.
+    Data parallel (world > 1): `pred2d` holds this rank's samples; the top-k and the mean run over the GLOBAL batch of
+    `numel_global` elements -- `all_gather(out [world, 32768], local [32768])` exchanges the ranks' histograms."""
     _want(pred2d, torch.bfloat16, "pred")
     _want(ref2d, torch.bfloat16, "ref")
     _want(loss_sum, torch.float64, "loss_sum")
@@ -468,12 +493,21 @@ def mse_outlier_fwd_bwd(pred2d, ref2d, row_mask, upstream, loss_sum, scratch: Ou
         _want(row_mask, torch.uint8, "row_mask")
     rows, cols = pred2d.shape
     numel = rows * cols
-    k = max(1, int(numel / 1000))
+    total = numel if numel_global is None else int(numel_global)
+    k = max(1, int(total / 1000))
     if want_grad and dpred is None:
         dpred = torch.empty_like(pred2d)
     lib = _lib.load()
     _check(lib.ar_absdiff_hist(_p(pred2d), _p(ref2d), numel, _p(scratch.hist), _stream()), "ar_absdiff_hist")
-    _check(lib.ar_topk_threshold(_p(scratch.hist), k, _p(scratch.sel), _stream()), "ar_topk_threshold")
-    _check(lib.ar_mse_outlier_fwd_bwd(_p(pred2d), _p(ref2d), _p(row_mask), rows, cols, float(upstream), _p(scratch.sel),
-                                      _p(loss_sum), _p(dpred if want_grad else None), _stream()), "ar_mse_outlier_fwd_bwd")
+    if world > 1:
+        if scratch.hist_all is None or scratch.hist_all.shape[0] != world:
+            scratch.hist_all = torch.zeros(world, scratch.hist.numel(), dtype=torch.int32, device=scratch.hist.device)
+        all_gather(scratch.hist_all, scratch.hist)
+        _check(lib.ar_topk_threshold_ranks(_p(scratch.hist_all), world, rank, _p(scratch.hist), k, _p(scratch.sel), _stream()),
+               "ar_topk_threshold_ranks")
+    else:
+        _check(lib.ar_topk_threshold(_p(scratch.hist), k, _p(scratch.sel), _stream()), "ar_topk_threshold")
+    _check(lib.ar_mse_outlier_fwd_bwd(_p(pred2d), _p(ref2d), _p(row_mask), rows, cols, 0 if numel_global is None else total,
+                                      float(upstream), _p(scratch.sel), _p(loss_sum), _p(dpred if want_grad else None),
+                                      _stream()), "ar_mse_outlier_fwd_bwd")
     return dpred

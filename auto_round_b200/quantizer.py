@@ -7,8 +7,11 @@ fp_outputs, q_inputs, block_ctx, input_ids=None)` mutates `block` in place (qdq 
 
 What is different from the reference (B200-first):
   * all tunables of a block live in ONE flat fp32 arena [V of every layer | scales of every layer] with a matching
-    gradient arena and best-snapshot arena, so the optimiser is one kernel and the data-parallel exchange is one
-    NCCL all-reduce per iteration;
+    best-snapshot arena; the weight gradient of every layer is the bf16 dWq of a plain tcgen05 GEMM, and ONE fused kernel
+    per layer turns it into (fake-quant backward -> snapshot -> sign-SGD step -> next iteration's fake-quant weight);
+  * under data parallelism a layer's dWq is reduce-scattered over the ranks as soon as its backward GEMMs are issued
+    (overlapping the rest of the backward), each rank updates its row shard of V / scales and the new fake-quant weight
+    is all-gathered: weight-sized work and memory traffic shrink with the number of GPUs;
   * loss, best-iteration selection, snapshot and sign-SGD update run on the device without any host
     synchronisation inside the 200-iteration loop (the reference calls loss.item() every iteration);
   * the sampler's batch sequence is drawn up-front (same python `random` stream, compressors/utils.py:388-438) and
@@ -66,9 +69,11 @@ def lr_schedule_table(iters: int, lr: float, minmax_lr: float) -> np.ndarray:
 
 
 class TuneArena:
-    """Flat fp32 storage for every tunable of one block: [ V_0 | V_1 | ... | scales ... ]."""
+    """Flat storage for every tunable of one block: fp32 [ V_0 | V_1 | ... | scales ... ] (+ the best snapshot) and the bf16
+    weight gradients `gq` [ dWq_0 | dWq_1 | ... ] written by the grad-w GEMMs.  `legacy_grads` adds the fp32/bf16 pre-sign
+    gradient buffers of the micro-batch path (fused grad-w epilogue -> ar_signsgd_step)."""
 
-    def __init__(self, specs: dict, device, grad_dtype=torch.float32):
+    def __init__(self, specs: dict, device, grad_dtype=None):
         off = 0
         self.views = {}
         for name, spec in specs.items():
@@ -86,20 +91,28 @@ class TuneArena:
         self.numel = off
         self.params = torch.zeros(off, dtype=torch.float32, device=device)
         self.params[self.clamp_begin:] = 1.0          # min/max_scale start at 1, V at 0 (wrapper.py:184-190)
-        # pre-sign gradients: rounding segment in `grad_dtype` (bf16 halves the data-parallel exchange; only the sign of
-        # the all-reduced sum is used), scale segment always fp32
-        self.grads_v = torch.zeros(self.clamp_begin, dtype=grad_dtype, device=device)
-        self.grads_s = torch.zeros(off - self.clamp_begin, dtype=torch.float32, device=device)
         self.best = torch.zeros(off, dtype=torch.float32, device=device)
+        self.gq_views, goff = {}, 0
+        for name, spec in specs.items():
+            self.gq_views[name] = (goff, spec.n * spec.k, (spec.n, spec.k))
+            goff += (spec.n * spec.k + 7) // 8 * 8    # 16-byte aligned segments (TMA store target)
+        self.gq = torch.zeros(goff, dtype=torch.bfloat16, device=device)
+        self.grads_v = self.grads_s = None
+        if grad_dtype is not None:
+            self.grads_v = torch.zeros(self.clamp_begin, dtype=grad_dtype, device=device)
+            self.grads_s = torch.zeros(off - self.clamp_begin, dtype=torch.float32, device=device)
 
     def layer_views(self, name: str) -> dict:
         out = {}
         for key, (o, n, shape) in self.views[name].items():
             out[key] = self.params[o:o + n].view(shape)
-            if key == "value":
-                out["grad_" + key] = self.grads_v[o:o + n].view(shape)
-            else:
-                out["grad_" + key] = self.grads_s[o - self.clamp_begin:o - self.clamp_begin + n].view(shape)
+            if self.grads_v is not None:
+                if key == "value":
+                    out["grad_" + key] = self.grads_v[o:o + n].view(shape)
+                else:
+                    out["grad_" + key] = self.grads_s[o - self.clamp_begin:o - self.clamp_begin + n].view(shape)
+        o, n, shape = self.gq_views[name]
+        out["gq"] = self.gq[o:o + n].view(shape)
         return out
 
     def best_views(self, name: str) -> dict:
@@ -108,8 +121,9 @@ class TuneArena:
 
 @dataclass
 class DataParallel:
-    """Calibration-sample sharding over the ranks of one NVSwitch box.  `group` may be a gloo
-    group in the CPU tests of the host logic."""
+    """Calibration-sample sharding over the ranks of one NVSwitch box.  The data path uses NCCL
+    (reduce-scatter / all-gather / all-reduce over NVLink); with a `gloo` group -- the CPU tests of the host logic and the
+    single-GPU two-process test of the sharded update -- the same calls are emulated with gloo's all-reduce / all-gather."""
     rank: int = 0
     world: int = 1
     group: object = None
@@ -117,12 +131,51 @@ class DataParallel:
     def shard(self, batch):
         return list(batch)[self.rank::self.world]
 
+    def row_shard(self, n_rows: int):
+        """Rows [r0, r1) of a layer's weight this rank owns in the sharded update, or None when the rows do not split
+        evenly (the layer then stays replicated: all-reduce of dWq + full update on every rank)."""
+        if self.world == 1 or n_rows % self.world:
+            return None
+        per = n_rows // self.world
+        return self.rank * per, (self.rank + 1) * per
+
+    def _nccl(self) -> bool:
+        import torch.distributed as dist
+        return dist.get_backend(self.group) == "nccl"
+
     def all_reduce_(self, *tensors):
         if self.world == 1:
             return
         import torch.distributed as dist
         for t in tensors:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            if t.dtype == torch.bfloat16 and not self._nccl():      # gloo: no bf16 reduction
+                f = t.float()
+                dist.all_reduce(f, op=dist.ReduceOp.SUM, group=self.group)
+                t.copy_(f)
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def reduce_scatter_(self, out, full):
+        """out (this rank's contiguous 1/world slice of `full`) <- sum over ranks."""
+        import torch.distributed as dist
+        if self._nccl():
+            dist.reduce_scatter_tensor(out, full, group=self.group)
+        else:
+            f = full.float()
+            dist.all_reduce(f, op=dist.ReduceOp.SUM, group=self.group)
+            out.copy_(f.reshape(self.world, -1)[self.rank].view_as(out))
+
+    def all_gather_(self, out, local):
+        """out [world * len(local)] <- every rank's `local` (which may be the rank's own slice of `out`)."""
+        import torch.distributed as dist
+        if self._nccl():
+            dist.all_gather_into_tensor(out, local, group=self.group)
+        else:                                                       # gloo has no all_gather on CUDA tensors: sum of
+            dt = torch.float32 if out.dtype == torch.bfloat16 else out.dtype      # zero-padded slices (exact)
+            buf = torch.zeros(out.numel(), dtype=dt, device=out.device)
+            buf.view(self.world, -1)[self.rank].copy_(local.reshape(-1))
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+            out.reshape(-1).copy_(buf)
 
 
 @dataclass
@@ -192,7 +245,7 @@ class SignRoundQuantizer:
         self.dp = dp or DataParallel()
         self.use_cuda_graph = use_cuda_graph
         self.fuse_block_ops = fuse_block_ops
-        self.grad_dtype = grad_dtype        # None: fp32 on one GPU, bf16 under data parallelism
+        self.grad_dtype = grad_dtype        # kept for API compatibility: the weight gradient is bf16 (autograd of F.linear)
         if gradient_accumulate_steps != 1:
             raise NotImplementedError("gradient_accumulate_steps != 1 (reference default is 1)")
         self.last_result: Optional[TuneResult] = None
@@ -251,8 +304,7 @@ class SignRoundQuantizer:
         if not todo:
             return {}, None
         device = next(iter(todo.values()))[0].weight.device
-        grad_dtype = self.grad_dtype if self.grad_dtype is not None else (torch.bfloat16 if self.dp.world > 1 else torch.float32)
-        arena = TuneArena({n: t[2] for n, t in todo.items()}, device, grad_dtype)
+        arena = TuneArena({n: t[2] for n, t in todo.items()}, device)
         wrapped = {}
         for name, (mod, sc, spec) in todo.items():
             gs = None if nv_global_scales is None else nv_global_scales.get(name)
@@ -402,12 +454,54 @@ class SignRoundQuantizer:
         clamp_hi = 2.0 if optimized else 1.0                        # minmax_scale_bound (sign_roundv2/quantizer.py:102)
         if optimized and len(optimized) != len(wrapped):
             raise NotImplementedError("enable_alg_ext with mixed optimized / plain layers in one block (per-layer bounds)")
-        if outlier_loss and dp.world > 1:
-            raise NotImplementedError("enable_alg_ext outlier-suppressed loss under data parallelism: the top-k is global over "
-                                      "the batch; a cross-rank histogram reduce is not built")
         outlier_scratch = ops.OutlierSelect(device) if outlier_loss else None
 
-        def fwd_bwd():
+        # ---- per-layer exchange + fused update.  One GPU: the update kernel follows the layer's backward GEMMs on the compute
+        # stream.  Data parallel: the layer's bf16 dWq is reduce-scattered on the communication stream while the backward
+        # continues, this rank updates its row shard (fake-quant backward, snapshot, sign-SGD, next Wq) and the new Wq rows
+        # are all-gathered; layers whose rows do not split evenly stay replicated (all-reduce + full update).
+        compute_stream = lambda: torch.cuda.current_stream(device)          # noqa: E731 (the capture stream while capturing)
+        comm = torch.cuda.Stream(device=device) if dp.world > 1 else None
+        best_of = {n: arena.best_views(n) for n in wrapped}
+        shards, gq_shard = {}, {}
+        for n, wl in wrapped.items():
+            wl.refresh_wq()                                         # iteration 0 runs on qdq(W; V = 0, scales = 1)
+            shards[n] = dp.row_shard(wl.spec.n)
+            if shards[n] is not None:
+                r0, r1 = shards[n]
+                gq_shard[n] = torch.empty(r1 - r0, wl.spec.k, dtype=torch.bfloat16, device=device)
+        # MoE under data parallelism: which experts receive a gradient differs per rank, so the collectives cannot be issued
+        # from the backward hooks (their order would differ); they run after the backward in layer order, and a layer no rank
+        # had a token for is skipped on the device (has_grad, summed over ranks)
+        deferred = has_moe and dp.world > 1
+        names = list(wrapped)
+        has_grad = torch.zeros(len(names), dtype=torch.int32, device=device) if deferred else None
+        name_of = {id(wl): n for n, wl in wrapped.items()}
+
+        def update_layer(wl, grad_flag=None):
+            n = name_of[id(wl)]
+            bv = best_of[n]
+            kw = dict(best_v=bv["value"], best_min=bv.get("min_scale"), best_max=bv["max_scale"], flag=flag, it_dev=it_dev,
+                      clamp_hi=clamp_hi, init_scale=wl.init_scale, has_grad=grad_flag)
+            args = (wl.spec, wl.weight, wl.value, wl.min_scale, wl.max_scale, wl.weight_min, wl.weight_max, wl.weight_global_scale)
+            if dp.world == 1:
+                ops.fq_update(*args, wl.gq, wl.wq, lr_tab, **kw)
+                return
+            comm.wait_stream(compute_stream())                      # this layer's dWq and dX GEMMs are enqueued
+            with torch.cuda.stream(comm):
+                if shards[n] is None:
+                    dp.all_reduce_(wl.gq)
+                    ops.fq_update(*args, wl.gq, wl.wq, lr_tab, **kw)
+                else:
+                    r0, r1 = shards[n]
+                    dp.reduce_scatter_(gq_shard[n], wl.gq)
+                    ops.fq_update(*args, gq_shard[n], wl.wq, lr_tab, row0=r0, row1=r1, gq_row0=r0, **kw)
+                    dp.all_gather_(wl.wq, wl.wq[r0:r1])
+
+        for wl in wrapped.values():
+            wl.on_grad = None if deferred else update_layer
+
+        def iteration(last: bool):
             ops.sched_load(idx_dev, inv_tab, it_dev, lbs, cur32, cur64, cur_inv)
             ops.gather_rows(x_all, cur32, out=x_buf)
             ops.gather_rows(ref_all, cur32, out=ref_buf)
@@ -418,43 +512,48 @@ class SignRoundQuantizer:
             if token_masks is not None:
                 mask_rows = token_masks.index_select(0, cur64).reshape(-1)
             for wl in wrapped.values():
-                wl.grad_accumulate = False
+                wl.got_grad = False
             pred = self.block_forward(block, x_buf, kw)
             pred2d = pred.reshape(-1, hidden)
             if pred2d.dtype != torch.bfloat16:
                 pred2d = pred2d.to(torch.bfloat16)
+            pred2d, ref2d = pred2d.contiguous(), ref_buf.reshape(-1, hidden)
             if outlier_loss:
-                dpred = ops.mse_outlier_fwd_bwd(pred2d.contiguous(), ref_buf.reshape(-1, hidden), mask_rows, 1000.0, loss_sum,
-                                                outlier_scratch)
+                dpred = ops.mse_outlier_fwd_bwd(pred2d, ref2d, mask_rows, 1000.0, loss_sum, outlier_scratch,
+                                                numel_global=gbs * seq * hidden if dp.world > 1 else None,
+                                                all_gather=dp.all_gather_, rank=dp.rank, world=dp.world)
             else:
-                dpred = ops.mse_fwd_bwd(pred2d.contiguous(), ref_buf.reshape(-1, hidden), None if unmasked_loss else mask_rows,
-                                        inv_numel, 1000.0, loss_sum)
-            pred.backward(dpred.view_as(pred).to(pred.dtype))
+                dpred = ops.mse_fwd_bwd(pred2d, ref2d, None if unmasked_loss else mask_rows, inv_numel, 1000.0, loss_sum)
 
-        def update(last: bool):
-            ops.best_update(loss_sum, inv_numel, 1.0, 0, state, flag, hist, inv_num_elm_dev=cur_inv, it_dev=it_dev)
-            if self.not_use_best_mse:
-                flag.fill_(1 if last else 0)
-            ops.signsgd_step(arena.params, arena.grads_v, arena.best, flag, lr_tab, 0, arena.clamp_begin, clamp_hi,
-                             it_dev=it_dev, g_scales=arena.grads_s)
+            def bookkeeping():                                      # loss -> best flag (read by every update kernel)
+                ops.best_update(loss_sum, inv_numel, 1.0, 0, state, flag, hist, inv_num_elm_dev=cur_inv, it_dev=it_dev)
+                if self.not_use_best_mse:
+                    flag.fill_(1 if last else 0)
+
+            if dp.world > 1:
+                comm.wait_stream(compute_stream())
+                with torch.cuda.stream(comm):
+                    dp.all_reduce_(loss_sum)                       # the best iteration is chosen on the GLOBAL loss
+                    bookkeeping()
+            else:
+                bookkeeping()
+            pred.backward(dpred.view_as(pred).to(pred.dtype))
+            if deferred:
+                has_grad.copy_(torch.tensor([1 if wrapped[n].got_grad else 0 for n in names], dtype=torch.int32), non_blocking=True)
+                for n in names:
+                    if not wrapped[n].got_grad:
+                        wrapped[n].gq.zero_()
+                dp.all_reduce_(has_grad)
+                for i, n in enumerate(names):
+                    update_layer(wrapped[n], has_grad[i:i + 1])
+            if dp.world > 1:
+                compute_stream().wait_stream(comm)
             ops.iter_advance(it_dev)
 
-        def eager_iteration(it):
-            fwd_bwd()
-            if has_moe:                                            # an expert that saw no token gets NO gradient
-                for wl in wrapped.values():                        # (sign_sgd.py:274-276 skips grad-is-None params)
-                    if not wl.grad_accumulate:
-                        wl.grad_value.zero_()
-                        wl.grad_max_scale.zero_()
-                        if wl.grad_min_scale is not None:
-                            wl.grad_min_scale.zero_()
-            dp.all_reduce_(arena.grads_v, arena.grads_s, loss_sum)   # pre-sign gradients + loss: one exchange
-            update(it == iters - 1)
-
         with fused_block_ops(block, self.fuse_block_ops):
-            # ---- CUDA graph: the iteration has static shapes and a device-side schedule, so (after two eager
-            # iterations that also serve as warm-up) it is captured once and replayed.  Under data parallelism the
-            # NCCL all-reduce stays outside the graph: [graph: fwd+bwd] -> all-reduce -> update kernels.
+            # ---- CUDA graph: the iteration has static shapes and a device-side schedule, so (after two eager iterations
+            # that also serve as warm-up) it is captured once -- forward, backward, the per-layer collectives on the
+            # communication stream and the fused updates -- and replayed.
             n_eager = min(iters, 2)
             use_graph = self.use_cuda_graph and not self.not_use_best_mse and iters > n_eager + 1 and not has_moe
             graph = None
@@ -463,22 +562,22 @@ class SignRoundQuantizer:
                 side.wait_stream(torch.cuda.current_stream(device))
                 with torch.cuda.stream(side):
                     for it in range(n_eager):
-                        eager_iteration(it)
+                        iteration(False)
                 torch.cuda.current_stream(device).wait_stream(side)
                 for wl in wrapped.values():
                     wl.anchor.grad = None
                 launches_before = ops.LAUNCHES[0]
                 try:
                     graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
-                        fwd_bwd()
-                        if dp.world == 1:
-                            update(False)
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local" if dp.world > 1 else "global"):
+                        iteration(False)
                 except Exception as e:  # noqa: BLE001 -- capture is an optimisation; the eager loop is the same kernels
                     import warnings
                     warnings.warn(f"CUDA graph capture of the SignRound iteration failed ({e!r}); running eagerly")
                     graph = None
                     torch.cuda.synchronize(device)
+                    if dp.world > 1:
+                        raise
             else:
                 n_eager = 0
             res.used_cuda_graph = graph is not None
@@ -487,12 +586,21 @@ class SignRoundQuantizer:
                 ops.LAUNCHES[0] += per_graph * (iters - n_eager) - per_graph
             for it in range(n_eager if use_graph else 0, iters):
                 if graph is None:
-                    eager_iteration(it)
+                    iteration(it == iters - 1)
                 else:
                     graph.replay()
-                    if dp.world > 1:
-                        dp.all_reduce_(arena.grads_v, arena.grads_s, loss_sum)
-                        update(it == iters - 1)
+        for wl in wrapped.values():
+            wl.on_grad = None
+        if dp.world > 1:            # every rank snapshotted its own row shard: rebuild the full best parameters
+            for n, wl in wrapped.items():
+                if shards[n] is None:
+                    continue
+                r0, r1 = shards[n]
+                kp, gpr = wl.spec.kpad, wl.spec.kpad // wl.spec.group_size
+                for key, t in best_of[n].items():
+                    flat = t.reshape(-1)
+                    per = kp if key == "value" else gpr
+                    dp.all_gather_(flat, flat[r0 * per:r1 * per])
 
         st = state.cpu().tolist()                                   # the only host sync of the block
         res.losses = hist.cpu().tolist()

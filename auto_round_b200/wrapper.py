@@ -4,10 +4,12 @@
 but the parameters are *views into one flat fp32 arena per block* (see quantizer.TuneArena) and the math runs in
 hand-written sm_100a kernels behind the C ABI:
 
-    forward   ar_fq_linear_fwd      qdq(W; V, scales) -> tcgen05 GEMM           (wrapper.py:517-565)
-    backward  ar_fq_linear_bwd_dx   dX = dY · Wq
-              ar_fq_linear_bwd_dw   dWq = dYᵀ·X with dV / d(min,max)_scale computed in the GEMM epilogue
-                                    (replaces autograd through wrapper.py:273-290)
+    forward   ar_gemm_bf16          Y = X · Wqᵀ on tcgen05; Wq = qdq(W; V, scales) is resident     (wrapper.py:517-565)
+    backward  ar_gemm_bf16          dWq = dYᵀ·X  (bf16, like autograd of F.linear)  and  dX = dY · Wq
+              ar_fq_update          ONE pass per layer: fake-quant backward from dWq (replaces autograd through
+                                    wrapper.py:273-290), best-param snapshot, sign-SGD step, and the NEXT iteration's Wq
+    (layers tuned with micro-batches -- lm_head -- use ar_fq_linear_fwd / ar_fq_linear_bwd_dw, whose GEMM epilogue
+     accumulates the fp32 dV directly)
 
 There is no autograd graph over the weight and no eager fallback.
 """
@@ -33,9 +35,7 @@ class _FQLinearFn(torch.autograd.Function):
         if x2d.dtype != torch.bfloat16:
             x2d = x2d.to(torch.bfloat16)
         x2d = x2d.contiguous()
-        y = ops.fq_linear_fwd(layer.spec, x2d, layer.weight, layer.value, layer.min_scale, layer.max_scale,
-                              layer.weight_min, layer.weight_max, layer.weight_global_scale, layer.bias_bf16,
-                              layer.wq, init_scale=layer.init_scale)
+        y = ops.gemm(x2d, layer.wq, bias=layer.bias_bf16)          # layer.wq is kept current by ar_fq_update
         ctx.layer = layer
         ctx.x_dtype = x.dtype
         ctx.save_for_backward(x2d)
@@ -49,16 +49,16 @@ class _FQLinearFn(torch.autograd.Function):
         if dy2d.dtype != torch.bfloat16:
             dy2d = dy2d.to(torch.bfloat16)
         dy2d = dy2d.contiguous()
-        ops.fq_linear_bwd_dw(layer.spec, dy2d, x2d, layer.weight, layer.value, layer.min_scale, layer.max_scale,
-                             layer.weight_min, layer.weight_max, layer.weight_global_scale, layer.grad_value,
-                             layer.grad_min_scale, layer.grad_max_scale, accumulate=layer.grad_accumulate,
-                             init_scale=layer.init_scale)
-        layer.grad_accumulate = True           # further micro-batches of this iteration add up
+        # dWq[N,K] = dYᵀ·X: A = dY stored [T,N] (MN-major), B = X stored [T,K] (MN-major); bf16 like autograd of F.linear
+        ops.gemm(dy2d, x2d, a_mn_major=True, b_mn_major=True, out=layer.gq)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.fq_linear_bwd_dx(layer.spec, dy2d, layer.wq).view(*dy.shape[:-1], layer.spec.k)
             if dx.dtype != ctx.x_dtype:
                 dx = dx.to(ctx.x_dtype)
+        layer.got_grad = True
+        if layer.on_grad is not None:          # the quantizer's per-layer exchange + fused update (after the dX GEMM:
+            layer.on_grad(layer)               # the update overwrites layer.wq with the next iteration's weight)
         return dx, torch.zeros((), dtype=torch.float32, device=dy.device), None
 
 
@@ -93,10 +93,13 @@ class WrapperLinear(nn.Module):
         self.value = arena_views["value"]
         self.max_scale = arena_views["max_scale"]
         self.min_scale = arena_views.get("min_scale")
-        self.grad_value = arena_views["grad_value"]
-        self.grad_max_scale = arena_views["grad_max_scale"]
+        self.gq = arena_views.get("gq")                     # bf16 [N,K]: dL/dWq of the current iteration
+        # micro-batch layers (quantize_layer): fp32 pre-sign gradients accumulated by the fused grad-w epilogue
+        self.grad_value = arena_views.get("grad_value")
+        self.grad_max_scale = arena_views.get("grad_max_scale")
         self.grad_min_scale = arena_views.get("grad_min_scale")
-        self.grad_accumulate = False
+        self.on_grad = None                                 # callback(layer) run at the end of this layer's backward
+        self.got_grad = False
         self.wq = torch.empty_like(self.weight)            # fake-quant weight of the current iteration
         self.anchor = torch.zeros((), dtype=torch.float32, device=w.device, requires_grad=True)
         self.params = {"value": self.value, "max_scale": self.max_scale}
@@ -105,6 +108,12 @@ class WrapperLinear(nn.Module):
 
     def forward(self, x):
         return _FQLinearFn.apply(x, self.anchor, self)
+
+    @torch.no_grad()
+    def refresh_wq(self):
+        """wq <- qdq(W; current V / scales): once before the loop; inside it ar_fq_update keeps wq current."""
+        ops.qdq_fwd(self.spec, self.weight, self.value, self.min_scale, self.max_scale, self.weight_min, self.weight_max,
+                    self.weight_global_scale, out_wq=self.wq, init_scale=self.init_scale)
 
     @torch.no_grad()
     def unwrapper(self, best: dict):

@@ -142,6 +142,26 @@ int ar_fq_linear_bwd_dw(const ar_qspec* q, const void* dy_bf16, const void* x_bf
                         int accumulate, void* stream);
 
 /*
+ * Fused per-layer update of the sign-SGD loop (one pass, 14 B/weight): given Gq = dL/dWq as bf16 [rows, K] -- the plain
+ * grad-w GEMM  ar_gemm_bf16(dY, X, a_mn_major=1, b_mn_major=1)  (autograd of F.linear rounds it to the weight dtype,
+ * auto_round/wrapper.py:470-481), or under data parallelism the reduce-scattered sum over ranks -- it performs, for rows
+ * [row0, row1) of the layer:
+ *   fake-quant backward (closed form of autograd through the @register_dtype function, wrapper.py:273-290)
+ *   -> if (*flag) best_* = PRE-update parameters (collect_best_params, compressors/utils.py:205-217)
+ *   -> p -= lr * sign(grad), min/max_scale clamped to [0, clamp_hi]            (SignSGD.step, sign_sgd.py:356-389)
+ *   -> wq_out rows = qdq(W; V', scales') for the next iteration's GEMMs          (WrapperLinear._qdq_weight)
+ * v [N,Kpad], min_scale (NULL for mx/nv), max_scale [G] are updated in place; gq is indexed from row gq_row0 (a rank's
+ * shard buffer starts at its first row).  dv_dbg/dmn_dbg/dmx_dbg (optional) receive the pre-sign gradients.
+ * has_grad (optional, device): *has_grad == 0 leaves the layer untouched (an expert no token was routed to gets no
+ * gradient and SignSGD skips it, sign_sgd.py:274-276).
+ */
+int ar_fq_update(const ar_qspec* q, const void* w_bf16, float* v, float* min_scale, float* max_scale,
+                 const void* wmin_bf16, const void* wmax_bf16, const float* gscale, const void* gq_bf16, int gq_row0,
+                 int row0, int row1, float* best_v, float* best_min_scale, float* best_max_scale, const int32_t* flag,
+                 const float* lr_table, int iter, const int32_t* it_ptr, float clamp_hi, void* wq_out_bf16,
+                 float* dv_dbg, float* dmn_dbg, float* dmx_dbg, const int32_t* has_grad, void* stream);
+
+/*
  * Masked MSE + its gradient in one pass (auto_round/.../sign_round/quantizer.py:127-158, :789-803):
  *   *loss_sum += sum(((pred*m) - (ref*m))^2)                       (double, UNnormalised, atomically accumulated)
  *   dpred = bf16( ((2*inv_numel) * ((pred*m) - (ref*m))) * upstream ) * m      upstream = 1000 (loss*1000).backward()
@@ -256,13 +276,22 @@ int ar_search_scale_mx(const void* w_bf16, const float* qw, long long qw_row_str
  *   ar_absdiff_hist:   hist[32768] (u32, zero before the first call) += histogram of the bf16 bit pattern of |pred - ref|
  *   ar_topk_threshold: from the histogram and k = max(1, numel / 1000): sel[0] = threshold pattern, sel[1] = how many elements
  *                      AT the threshold are dropped, sel[2] = 0 (tie counter); re-zeroes hist
+ *   ar_topk_threshold_ranks: data-parallel form.  hist_all = the `world` ranks' histograms [world, 32768] (one all-gather);
+ *                      the threshold comes from their sum (the top-k is global over the batch) and the ties at the threshold
+ *                      are handed out in rank order so that exactly k elements are dropped over all ranks; re-zeroes
+ *                      hist_local (this rank's histogram)
  *   ar_mse_outlier_fwd_bwd: loss_sum (double, unnormalised) += sum((|pred-ref| * row_mask * keep)^2); dpred (bf16, nullable)
  *                      = d(upstream * mean(...)) / d pred.  keep drops patterns > sel[0] and the first sel[1] found at sel[0].
+ *                      numel_total > 0: the mean runs over that many elements (the global batch of a data-parallel
+ *                      iteration) instead of rows * cols.
  */
 int ar_absdiff_hist(const void* pred_bf16, const void* ref_bf16, int64_t numel, uint32_t* hist, void* stream);
 int ar_topk_threshold(uint32_t* hist, int64_t k, uint32_t* sel, void* stream);
+int ar_topk_threshold_ranks(const uint32_t* hist_all, int world, int rank, uint32_t* hist_local, int64_t k, uint32_t* sel,
+                            void* stream);
 int ar_mse_outlier_fwd_bwd(const void* pred_bf16, const void* ref_bf16, const uint8_t* row_mask, int64_t rows, int64_t cols,
-                           float upstream, uint32_t* sel, double* loss_sum, void* dpred_bf16, void* stream);
+                           int64_t numel_total, float upstream, uint32_t* sel, double* loss_sum, void* dpred_bf16,
+                           void* stream);
 /* importance matrix: imatrix[k] += sum over rows of x[row,k]^2 (algorithms/quantization/rtn/quantizer.py:86-105) */
 int ar_imatrix_accum(const void* x_bf16, long long rows, int k, float* imatrix, void* stream);
 

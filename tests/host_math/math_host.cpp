@@ -1,13 +1,14 @@
 // TEST INFRASTRUCTURE: the product's device math header (auto_round_b200/csrc/ar_qdq_math.cuh) compiled as plain host C++
 // (g++, no nvcc, no GPU) behind a C entry point, so that the fake-quant forward/backward formulas -- including the
 // enable_alg_ext init_scale branches that have not run on hardware yet -- can be checked against the oracle in the CPU
-// test tier.  The CUDA headers provide host versions of the fp16 / bf16 / e4m3 conversions; the only shim is
-// __uint_as_float.  Group handling mirrors qdq_fwd_kernel / qdq_bwd_kernel (ar_qdq.cu): wmin/wmax clamped at 0, fp4 amax,
+// test tier.  The CUDA headers provide host versions of the fp16 / bf16 / e4m3 conversions; the only shims are
+// __uint_as_float and __fmaf_rn.  Group handling mirrors qdq_fwd_kernel / qdq_bwd_kernel (ar_qdq.cu): wmin/wmax clamped at 0, fp4 amax,
 // sequential (not shuffle-tree) group sums.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 #include "../../auto_round_b200/csrc/ar_qdq_math.cuh"
 
 namespace {
@@ -54,4 +55,35 @@ extern "C" int host_qdq(int dtype, int bits, int g, long groups, const float* w,
     case 3: run<ar::NvFp4, true>(bits, g, groups, w, v, mn, mx, init, gscale, thr, gq, wq, scale, zp, dv, dmin, dmax); return 0;
   }
   return -1;
+}
+
+// Exhaustive check of ar::div_exact (the division-free w / s of the hot kernels): every finite bf16 numerator against every
+// finite fp16-valued scale with |s| >= 1e-5 (the q_scale_thresh clip guarantees that bound), bit-for-bit against the IEEE
+// quotient.  Returns the number of mismatching pairs; *pairs receives how many were checked.
+extern "C" long host_div_exact_check(long* pairs) {
+  long bad = 0, tot = 0;
+#pragma omp parallel for reduction(+ : bad, tot) schedule(dynamic, 64)
+  for (int hs = 0; hs < 65536; ++hs) {
+    const int e = (hs >> 10) & 31, m = hs & 1023;
+    if (e == 31) continue;
+    float s = (e == 0) ? ldexpf((float)m, -24) : ldexpf((float)(m | 1024), e - 25);
+    if (hs & 0x8000) s = -s;
+    if (!(fabsf(s) >= 1.0e-5f)) continue;
+    volatile float one = 1.f;
+    const float rs = one / s;
+    for (int wb = 0; wb < 65536; ++wb) {
+      const float w = __uint_as_float(((uint32_t)wb) << 16);
+      if (std::isnan(w) || std::isinf(w)) continue;
+      volatile float wv = w, sv = s;
+      const float ref = wv / sv;
+      const float got = ar::div_exact(w, s, rs);
+      uint32_t a, b;
+      memcpy(&a, &got, 4);
+      memcpy(&b, &ref, 4);
+      ++tot;
+      if (a != b) ++bad;
+    }
+  }
+  if (pairs) *pairs = tot;
+  return bad;
 }

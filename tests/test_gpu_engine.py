@@ -136,14 +136,15 @@ def test_sign_agreement_iteration0(golden_dir):
     blk = _tiny_block(b["block_state"], DEV)
     for p in blk.parameters():
         p.requires_grad_(False)
-    q = SignRoundQuantizer(parse_scheme("W4A16", {"group_size": 32}), iters=1, batch_size=4)
+    # one iteration with lr = 1: V' = 0 - 1 * sign(dV), so the arena holds -sign(dV) of the fused update kernel
+    q = SignRoundQuantizer(parse_scheme("W4A16", {"group_size": 32}), iters=1, batch_size=4, lr=1.0)
     q.quantize_block(blk, [t.to(DEV) for t in b["inputs"]], b["others"], [t.to(DEV) for t in b["fp_outputs"]], None, None,
                      input_ids=b["input_ids"], sampler=S.ReplaySampler([idx]), keep_arena=True)
     arena, names = q.last_arena, q.last_result.quantized_layers
     agree_all, n_all = 0.0, 0
     for name in names:
         o, n, shape = arena.views[name]["value"]
-        g = arena.grads_v[o:o + n].view(shape).float().cpu()
+        g = -arena.params[o:o + n].view(shape).float().cpu()
         ref = wrapped[name].value.grad.reshape(shape)
         big = ref.abs() > 0.05 * ref.abs().max()
         agree_all += float((torch.sign(g)[big] == torch.sign(ref)[big]).sum())

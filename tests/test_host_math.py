@@ -24,7 +24,7 @@ def host_math(tmp_path_factory):
         pytest.skip("CUDA headers not found")
     out = str(tmp_path_factory.mktemp("hostmath") / "libmath_host.so")
     src = os.path.join(HERE, "host_math", "math_host.cpp")
-    subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", f"-I{CUDA_INC}", src, "-o", out],
+    subprocess.run(["g++", "-std=c++17", "-O1", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", f"-I{CUDA_INC}", src, "-o", out],
                    check=True)
     lib = C.CDLL(out)
     F = C.POINTER(C.c_float)
