@@ -21,6 +21,7 @@
 
 #include <stdlib.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "ar_qdq_math.cuh"
@@ -196,6 +197,41 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                : "memory");
 }
 
+// ---- cluster-scope variants used by the dynamic tile scheduler (ticket written into the peer CTA's shared memory)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP_C:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_C;\n"
+      "bra WAIT_LOOP_C;\n"
+      "DONE_C:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 remaddr;\n"
+      "mapa.shared::cluster.u32 remaddr, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remaddr];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void st_shared_cluster_u32(const void* local_addr, uint32_t cta, uint32_t value) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 remaddr;\n"
+      "mapa.shared::cluster.u32 remaddr, %0, %1;\n"
+      "st.shared::cluster.u32 [remaddr], %2;\n"
+      "}\n" ::"r"(smem_u32(local_addr)),
+      "r"(cta), "r"(value)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -239,6 +275,7 @@ struct GemmParams {
   int m, n, k;                    // logical problem: D[m,n] = A[m,k] B[n,k]^T
   int m_tiles, n_tiles;
   const uint16_t* bias;           // EPI_STORE, optional [n]
+  unsigned int* tile_ctr;         // dynamic tile scheduler: ticket counter of this launch (0 at launch, reset to 0 at exit)
   DwParams dw;
 };
 
@@ -256,8 +293,9 @@ struct SmemLayout {
   static constexpr int kBOff = kNumStages * kABytes;
   static constexpr int kCOff = kBOff + kNumStages * kBBytes;
   static constexpr int kBarOff = kCOff + 2 * kCBytes;
-  static constexpr int kTotal = kBarOff + 256;
+  static constexpr int kTotal = kBarOff + 512;
 };
+constexpr int kSchedSlots = 8;
 
 // tile order: groups of 8 M-tiles sweep all N-tiles, so the ~148 concurrent CTAs share A/B tiles in L2
 __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int& mt, int& nt) {
@@ -396,6 +434,14 @@ __device__ __forceinline__ void epilogue_dw(const GemmParams& p, uint32_t tmem_a
 }
 
 // ------------------------------------------------------------------------------------------- the kernel
+// Tile scheduling is DYNAMIC: the scheduling unit (a CTA, or the CTA pair of cta_group::2) draws tile tickets from a
+// global counter (one atomicAdd per tile, issued one tile ahead by the TMA-producer thread of the leader CTA) and publishes
+// each ticket to its consumers -- MMA warp, epilogue warps, the peer CTA's producer and epilogue -- through a small
+// shared-memory ring with full/empty mbarriers (the peer's copy is written through distributed shared memory).
+// With static striding a CTA that starts late still owns its full share of tiles; that is exactly what happens when NCCL
+// kernels of the data-parallel exchange hold a few SMs while a GEMM launches (they cannot co-reside with a 200 KB CTA).
+// With tickets, late CTAs simply find the queue empty.  Ticket order = rasterised tile order, so concurrently running
+// units still work on neighbouring tiles (L2 reuse).  The unit that draws the last terminal ticket resets the counter.
 template <bool A_MN, bool B_MN, int BN, int EPI, class Ctx, int G, bool IS_FP4, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -409,16 +455,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   uint64_t* tfull = bars + 2 * kNS;        // [2]
   uint64_t* tempty = bars + 2 * kNS + 2;   // [2]     (CG == 2: only the leader's)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNS + 4);
+  uint64_t* sfull = bars + 2 * kNS + 5;    // [kSchedSlots] ticket published (one per CTA)
+  uint64_t* sempty = sfull + kSchedSlots;  // [kSchedSlots] ticket consumed by everyone (the leader's are waited on)
+  volatile int32_t* stile = reinterpret_cast<volatile int32_t*>(sempty + kSchedSlots);   // [kSchedSlots]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;     // rank inside the CTA pair
   const bool leader = (cta_rank == 0);
-  const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // scheduling unit: CTA or CTA pair
-  const int num_units = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_units = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;   // scheduling unit: CTA or CTA pair
   const int num_tiles = p.m_tiles * p.n_tiles;     // m_tiles counts (128*CG)-row tiles
   const int num_kb = (p.k + BLOCK_K - 1) / BLOCK_K;
   constexpr uint32_t kTmemCols = 2 * BN;       // two accumulator stages (256 or 512: powers of two)
+  // consumers of a ticket: leader MMA warp + 4 epilogue warps (+ the peer's producer and its 4 epilogue warps)
+  constexpr uint32_t kTicketConsumers = (CG == 2) ? 10u : 5u;
 
   if (warp == kProducerWarp && lane == 0) {
     prefetch_tmap(&map_a);
@@ -426,6 +476,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     if (EPI == EPI_STORE) prefetch_tmap(&map_d);
     for (int i = 0; i < kNS; ++i) { mbar_init(&full[i], CG); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CG * kEpiThreads); }
+    for (int i = 0; i < kSchedSlots; ++i) { mbar_init(&sfull[i], 1); mbar_init(&sempty[i], kTicketConsumers); }
     fence_barrier_init();
   }
   if (CG == 2) cluster_sync();                 // peer barriers are initialised before anyone arrives remotely
@@ -437,11 +488,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // ticket consumer: wait for slot `n % kSchedSlots`, read the tile id, hand the slot back (one arrival per warp / thread)
+  auto take_ticket = [&](uint32_t n, bool arrive, bool whole_warp) -> int {
+    const uint32_t slot = n % kSchedSlots, ph = (n / kSchedSlots) & 1u;
+    if (CG == 2) mbar_wait_cluster(&sfull[slot], ph); else mbar_wait(&sfull[slot], ph);
+    const int t = stile[slot];
+    if (whole_warp) __syncwarp();                           // every lane of the warp has read the slot
+    if (arrive) {
+      if (CG == 2) mbar_arrive_release_cluster(&sempty[slot], 0); else mbar_arrive(&sempty[slot]);
+    }
+    return t;
+  };
+
   if (warp == kProducerWarp) {
-    // ===================================================================== TMA producer
+    // ===================================================================== TMA producer (+ ticket scheduler in the leader)
     if (elect_one()) {
-      uint32_t it = 0;
-      for (int t = unit; t < num_tiles; t += num_units) {
+      uint32_t it = 0, n = 0;
+      int t = 0, t_next = 0;
+      if (leader) t = (int)atomicAdd(p.tile_ctr, 1u);
+      for (;; ++n) {
+        if (leader) {
+          const uint32_t slot = n % kSchedSlots, ph = (n / kSchedSlots) & 1u;
+          mbar_wait(&sempty[slot], ph ^ 1u);                 // all consumers are done with the ticket 8 tiles back
+          stile[slot] = t;
+          if (CG == 2) {
+            st_shared_cluster_u32(const_cast<const int32_t*>(&stile[slot]), 1, (uint32_t)t);
+            mbar_arrive_release_cluster(&sfull[slot], 1);
+            mbar_arrive_release_cluster(&sfull[slot], 0);
+          } else {
+            mbar_arrive(&sfull[slot]);
+          }
+          if (t >= num_tiles) break;
+          t_next = (int)atomicAdd(p.tile_ctr, 1u);           // next ticket: in flight while this tile's loads are issued
+        } else {
+          t = take_ticket(n, true, false);
+          if (t >= num_tiles) break;
+        }
         int mt, nt;
         tile_coords(t, p.m_tiles, p.n_tiles, mt, nt);
         const int m0 = mt * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M;        // this CTA's 128 rows of A / D
@@ -473,7 +555,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               load(sb + i * (64 * BLOCK_K * 2), &map_b, n0 + i * 64, k0);
           }
         }
+        if (leader) t = t_next;
       }
+      // every unit draws exactly one terminal ticket; the holder of the LAST one re-arms the counter for the next launch
+      if (leader && t == num_tiles + num_units - 1) atomicExch(p.tile_ctr, 0u);
     }
   } else if (warp == kMmaWarp && leader) {
     // ===================================================================== MMA issuer (leader CTA of a pair)
@@ -482,8 +567,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     // MN-major: SBO = 8 k-rows * 128 B, LBO = 64 k-rows * 128 B (next 64-wide MN atom); K step (16 rows) = +2048 B
     constexpr uint32_t a_lbo = A_MN ? (BLOCK_K * 128) : 0, b_lbo = B_MN ? (BLOCK_K * 128) : 0;
     constexpr uint32_t a_kstep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2), b_kstep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
-    uint32_t it = 0, local_tile = 0;
-    for (int t = unit; t < num_tiles; t += num_units, ++local_tile) {
+    uint32_t it = 0;
+    for (uint32_t local_tile = 0;; ++local_tile) {
+      const int t = take_ticket(local_tile, lane == 0, true);
+      if (t >= num_tiles) break;
       const uint32_t as = local_tile & 1u, aph = (local_tile >> 1) & 1u;
       mbar_wait(&tempty[as], aph ^ 1u);
       tc_fence_after();
@@ -518,8 +605,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int q = warp & 3;                                // TMEM lane quarter this warp may access
     const int row_in_tile = q * 32 + lane;
     const int epi_tid = threadIdx.x - kEpiFirstWarp * 32;
-    uint32_t local_tile = 0, store_idx = 0;
-    for (int t = unit; t < num_tiles; t += num_units, ++local_tile) {
+    uint32_t store_idx = 0;
+    for (uint32_t local_tile = 0;; ++local_tile) {
+      const int t = take_ticket(local_tile, lane == 0, true);
+      if (t >= num_tiles) break;
       int mt, nt;
       tile_coords(t, p.m_tiles, p.n_tiles, mt, nt);
       const int m0 = mt * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M, n0 = nt * BN;
@@ -640,6 +729,25 @@ static int check_device() {
   return AR_OK;
 }
 
+// ticket counters of the dynamic tile scheduler: one per launch in flight, handed out round-robin (a counter is back at 0
+// when its kernel exits; 1024 launches later nothing of that kernel is still running on any stream)
+constexpr int kCtrSlots = 1024;
+__device__ unsigned int g_tile_ctr[kCtrSlots];
+
+static unsigned int* next_tile_counter() {
+  static unsigned int* base[64] = {nullptr};
+  static std::atomic<unsigned> next{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (base[dev] == nullptr) {
+    void* ptr = nullptr;
+    if (cudaGetSymbolAddress(&ptr, g_tile_ctr) != cudaSuccess) return nullptr;
+    base[dev] = (unsigned int*)ptr;
+  }
+  return base[dev] + (next.fetch_add(1) % kCtrSlots);
+}
+
 template <bool A_MN, bool B_MN, int BN, int EPI, class Ctx, int G, bool IS_FP4, int CG>
 static int launch_cg(const void* a, const void* b, void* d, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
                      const GemmParams& base, cudaStream_t st) {
@@ -667,6 +775,8 @@ static int launch_cg(const void* a, const void* b, void* d, int m, int n, int k,
   }
   GemmParams p = base;
   p.m = m; p.n = n; p.k = k;
+  p.tile_ctr = next_tile_counter();
+  AR_REQUIRE(p.tile_ctr != nullptr, AR_E_DRIVER, "tile counter symbol not available on this device");
   p.m_tiles = (m + BLOCK_M * CG - 1) / (BLOCK_M * CG);
   p.n_tiles = (n + BN - 1) / BN;
   const int tiles = p.m_tiles * p.n_tiles;

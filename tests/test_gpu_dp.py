@@ -88,7 +88,7 @@ def _first_step(rank, world, dev, tag, scheme_kw):
     return a.params[:a.clamp_begin].detach().cpu(), a
 
 
-def _worker(rank, world, port, backend, tag, scheme_kw, alg_ext, out):
+def _worker(rank, world, port, backend, tag, scheme_kw, alg_ext, out_dir):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -113,10 +113,10 @@ def _worker(rank, world, port, backend, tag, scheme_kw, alg_ext, out):
         full = full.to(dev)
         dist.all_reduce(full)
         r["v1"] = full.cpu()
-        out.put((rank, "ok", r))
+        torch.save(("ok", r), os.path.join(out_dir, f"rank{rank}.pt"))
     except Exception as e:  # noqa: BLE001
         import traceback
-        out.put((rank, "error: " + repr(e) + "\n" + traceback.format_exc(), None))
+        torch.save(("error: " + repr(e) + "\n" + traceback.format_exc(), None), os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
         if dist.is_initialized():
             dist.destroy_process_group()
@@ -127,21 +127,24 @@ CASES = {"w4a16_sym_g32": (dict(scheme="W4A16", group_size=32), False),
          "algext_w2a16_sym_g32": (dict(scheme="W2A16", group_size=32), True)}
 
 
-def _check(tag, backend, world=2):
+def _check(tag, backend, tmp_path, world=2):
     scheme_kw, alg_ext = CASES[tag]
     ctx = mp.get_context("spawn")
-    out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, tag, scheme_kw, alg_ext, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, tag, scheme_kw, alg_ext, str(tmp_path)))
+             for r in range(world)]
     for p in procs:
         p.start()
+    for p in procs:
+        p.join(timeout=600)
+        assert not p.is_alive(), "data-parallel worker hung"
     got = {}
-    for _ in range(world):
-        rank, status, r = out.get(timeout=600)
+    for rank in range(world):
+        f = os.path.join(str(tmp_path), f"rank{rank}.pt")
+        assert os.path.exists(f), f"rank {rank} died without a result (exit code {procs[rank].exitcode})"
+        status, r = torch.load(f, weights_only=False)
         assert status == "ok", f"rank {rank}: {status}"
         got[rank] = r
-    for p in procs:
-        p.join(timeout=60)
     dev = torch.device("cuda", 0)
     one = _tune(0, 1, dev, tag, scheme_kw, ITERS, graph=(backend == "nccl"), alg_ext=alg_ext)
     v1_one, _ = _first_step(0, 1, dev, tag, scheme_kw)
@@ -162,11 +165,11 @@ def _check(tag, backend, world=2):
 
 
 @pytest.mark.parametrize("tag", list(CASES))
-def test_two_ranks_one_gpu_gloo_equals_one_rank(tag):
-    _check(tag, "gloo")
+def test_two_ranks_one_gpu_gloo_equals_one_rank(tag, tmp_path):
+    _check(tag, "gloo", tmp_path)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="one rank per GPU over NCCL needs >= 2 GPUs (gpurun --gpus 2)")
 @pytest.mark.parametrize("tag", ["w4a16_sym_g32", "algext_w2a16_sym_g32"])
-def test_two_ranks_nccl_graph_equals_one_rank(tag):
-    _check(tag, "nccl")
+def test_two_ranks_nccl_graph_equals_one_rank(tag, tmp_path):
+    _check(tag, "nccl", tmp_path)
