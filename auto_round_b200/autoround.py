@@ -299,7 +299,9 @@ class AutoRound:
             raise _StopForward
 
         # only what runs before the first block needs the device: everything except the other blocks
-        _, blocks = find_blocks(model)
+        blocks = getattr(self, "_blocks", None)
+        if blocks is None:
+            _, blocks = find_blocks(model)
         moved = []
         for name, mod in model.named_children():
             moved.append(mod)
@@ -394,6 +396,23 @@ class AutoRound:
         full = torch.empty((per * dp.world,) + tuple(local.shape[1:]), dtype=local.dtype, device=dev)
         dist.all_gather_into_tensor(full, local.contiguous(), group=dp.group)
         return list(torch.split(full[:n], 1, dim=0))
+
+    def _block_mse(self, outs, refs, token_masks):
+        """mean over valid tokens of (out - ref)^2, fp32 accumulate (ar_mse_fwd_bwd without the gradient) -> device scalar."""
+        loss = torch.zeros(1, dtype=torch.float64, device=self.device)
+        hidden = outs[0].shape[-1]
+        for i in range(0, len(outs), self.batch_size):
+            o = torch.cat([t.to(self.device) for t in outs[i:i + self.batch_size]], dim=0).reshape(-1, hidden).contiguous()
+            r = torch.cat([t.to(self.device) for t in refs[i:i + self.batch_size]], dim=0).reshape(-1, hidden).contiguous()
+            m = None
+            if token_masks is not None:
+                m = torch.cat([t.reshape(-1) for t in token_masks[i:i + self.batch_size]]).to(torch.uint8).contiguous()
+            ops.mse_fwd_bwd(o, r, m, 1.0, 1.0, loss, want_grad=False)
+        if token_masks is not None:
+            n_valid = torch.stack([t.sum() for t in token_masks]).sum().to(torch.float64)      # device count
+        else:
+            n_valid = torch.tensor(float(len(outs) * outs[0].shape[-2]), dtype=torch.float64, device=self.device)
+        return (loss / (n_valid * hidden)).reshape(())
 
     @staticmethod
     def _fuse_nv_global_scales(block: nn.Module, names) -> dict:
@@ -498,6 +517,9 @@ class AutoRound:
                 q_inputs = self._forward_all(quantizer, block, eff, others, token_masks)
             else:
                 q_inputs = None
+            # per-block output MSE of the tuned block against the FP block over ALL samples (valid tokens only) -- the second
+            # half of the headline metric; a device scalar, read back after the last block (no host sync here)
+            blk_mse = self._block_mse(q_inputs, ref_out, token_masks) if q_inputs is not None else None
             fp_inputs = ref_out
             ev[3].record()
             if self._pack_on_the_fly:                                     # immediate_pack (orchestrator.py:327-337)
@@ -516,11 +538,15 @@ class AutoRound:
             phases = {k: ev[i].elapsed_time(ev[i + 1]) for i, k in enumerate(("ref_forward_ms", "tune_ms", "q_forward_ms", "pack_ms"))}
             self.block_results.append({"block": f"{prefix}.{bi}", "init_loss": res.init_loss, "best_loss": res.best_loss,
                                        "best_iter": res.best_iter, "seconds": time.time() - tb, "losses": res.losses,
-                                       "phases_ms": phases, "cuda_graph": res.used_cuda_graph})
+                                       "phases_ms": phases, "cuda_graph": res.used_cuda_graph, "batches": res.batches,
+                                       "block_mse": blk_mse})
         self._lm_head_extra = None
         if self.quant_lm_head:
             self._quantize_lm_head(quantizer, fp_inputs, q_inputs, ids_cache)
         self.timings["tuning_s"] = time.time() - t0                      # "quantization tuning time" (orchestrator.py:792)
+        for r in self.block_results:                                      # device scalars -> python floats
+            if isinstance(r.get("block_mse"), torch.Tensor):
+                r["block_mse"] = float(r["block_mse"])
         if resume is not None and self.dp.rank == 0:
             resume.clear()                                                # a finished run leaves no state behind
         self.quantized = True

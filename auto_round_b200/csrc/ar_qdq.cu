@@ -316,7 +316,10 @@ struct UpdArgs {
   const int32_t* has_grad; // optional: *has_grad == 0 -> the layer received no gradient this iteration: leave it untouched
 };
 
-__device__ __forceinline__ float sgnf(float g) { return (g > 0.f) ? 1.f : ((g < 0.f) ? -1.f : 0.f); }
+// p - lr * sign(g): sign(0) = sign(NaN) = 0 like the kernels of ar_loop.cu
+__device__ __forceinline__ float sign_step(float p, float lr, float g) {
+  return (g > 0.f || g < 0.f) ? p - copysignf(lr, g) : p;
+}
 
 template <class Ctx, int G, bool IS_FP4>
 __global__ void __launch_bounds__(kThreads) fq_update_kernel(QArgs a, UpdArgs u) {
@@ -369,11 +372,11 @@ __global__ void __launch_bounds__(kThreads) fq_update_kernel(QArgs a, UpdArgs u)
   }
   // sign-SGD step (every lane of a group derives the same new scales from the shuffled group sums)
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = v[i] - lr_v * sgnf(d[i]);
+  for (int i = 0; i < 8; ++i) v[i] = sign_step(v[i], lr_v, d[i]);
   *reinterpret_cast<float4*>(u.v + voff) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(u.v + voff + 4) = make_float4(v[4], v[5], v[6], v[7]);
-  gi.mx = clampf(gi.mx - lr_s * sgnf(gmx), 0.f, u.clamp_hi);
-  if (u.mn) gi.mn = clampf(gi.mn - lr_s * sgnf(gmn), 0.f, u.clamp_hi);
+  gi.mx = clampf(sign_step(gi.mx, lr_s, gmx), 0.f, u.clamp_hi);
+  if (u.mn) gi.mn = clampf(sign_step(gi.mn, lr_s, gmn), 0.f, u.clamp_hi);
   if (lead) {
     u.mx[gidx] = gi.mx;
     if (u.mn) u.mn[gidx] = gi.mn;

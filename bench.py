@@ -1,23 +1,32 @@
-"""bench.py -- Llama-3-8B W4A16 (sym, g128) block-wise SignRound calibration on B200.
+"""bench.py -- block-wise SignRound calibration on B200; headline: Llama-3-8B W4A16 (sym, g128), BASELINE.json configs[1].
 
-    python bench.py --gpus N --steps K --warmup W            # our arm  (torchrun for N > 1)
-    python bench.py --impl reference --gpus N --steps K --warmup W    # the reference's CPU path (oracle port)
+    python bench.py --gpus N --steps K --warmup W [--config NAME]      # our arm  (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W     # the reference's CPU path (oracle port)
 
-A STEP is one transformer block of Llama-3-8B taken through the whole hot path exactly as the reference's
-`quantization tuning time` span counts it (compressors/orchestrator.py:631 -> 792): FP reference forward over all
-128 calibration samples, 200 sign-SGD iterations (batch 8 x 2048 tokens), forward of the tuned block (next block's
-inputs), unwrap, INT4 pack.  All 32 blocks have the same shapes, so `value` (seconds for the 32-block model) is
-ms_per_step * 32; with --steps 32 it is measured outright.  Weights are random-init (HF default init, seed 0),
-calibration tokens are synthetic (seed 1): there is no network.
+A STEP is one transformer block taken through the whole hot path exactly as the reference's `quantization tuning time`
+span counts it (compressors/orchestrator.py:631 -> 792): FP reference forward over all 128 calibration samples, `iters`
+sign-SGD iterations (batch 8 x 2048 tokens), forward of the tuned block (next block's inputs), unwrap, low-bit pack.  All
+blocks of a model have the same shapes, so `value` (seconds for the whole model) is ms_per_step * n_blocks; with --steps
+n_blocks it is measured outright.  Weights are random-init (HF default init, seed 0), calibration tokens are synthetic
+(seed 1): there is no network.
 
 Both numbers come from ONE pass through the public API `AutoRound(model_on_host, ...).quantize()`:
   e2e    device time of the whole per-block span: H2D of the block's bf16 weights from pinned host memory ->
-         compute -> D2H of the packed int4 tensors (CUDA events, max over ranks)
+         compute -> D2H of the packed tensors (CUDA events, max over ranks)
   value  the same span minus the H2D / D2H segments (inputs already resident in HBM)
+Beside them (N = 1), each outside the timed region:
+  roofline              the GEMM launch mix of one iteration replayed alone (vs the BURST cuBLAS peak) and, under CUPTI, inside
+                        a running iteration (vs the SUSTAINED peak)
+  per_block_mse_vs_ref  block 0 tuned by the reference's algorithm (oracle/, torch eager on the same GPU, same batches):
+                        final output MSE of both against the FP block -- the second half of BASELINE.json's metric
+  gpu_eager_baseline    the reference's own GPU path (eager ATen + cuBLAS + autograd through the fake-quant graph, i.e. the
+                        oracle on `cuda`) per iteration at the full shape -- what a user has today on this GPU
+  cpu_baseline          the reference's CPU path on the host cores, bounded sample (see cpu_steps)
 """
 from __future__ import annotations
 
 import argparse
+import copy
 import json
 import os
 import subprocess
@@ -30,23 +39,54 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-LLAMA3_8B = dict(hidden_size=4096, intermediate_size=14336, num_attention_heads=32, num_key_value_heads=8,
-                 vocab_size=128256, rope_theta=500000.0, rms_norm_eps=1e-5, max_position_embeddings=8192)
-N_BLOCKS_FULL = 32
-ITERS, NSAMPLES, SEQLEN, BATCH = 200, 128, 2048, 8
-P_BLOCK = 218_103_808
-P_QKV = 25_165_824
-# linear-layer FLOPs of one step (one block): 200 iterations + 2 full-set forwards
-FLOPS_PER_STEP = ITERS * (BATCH * SEQLEN) * (6 * P_BLOCK - 2 * P_QKV) + 2 * 2 * (NSAMPLES * SEQLEN) * P_BLOCK
+NSAMPLES, SEQLEN, BATCH = 128, 2048, 8
+
+# BASELINE.json configs.  `linears`: (name, N, K, input needs a gradient) of one block.
+_LLAMA_LIN = [("q", 4096, 4096, False), ("k", 1024, 4096, False), ("v", 1024, 4096, False), ("o", 4096, 4096, True),
+              ("gate", 14336, 4096, True), ("up", 14336, 4096, True), ("down", 4096, 14336, True)]
+_QWEN_LIN = [("q", 3584, 3584, False), ("k", 512, 3584, False), ("v", 512, 3584, False), ("o", 3584, 3584, True),
+             ("gate", 18944, 3584, True), ("up", 18944, 3584, True), ("down", 3584, 18944, True)]
+CONFIGS = {
+    "llama3_8b_w4a16": dict(
+        metric="Llama-3-8B W4A16 calib wall-clock (s) @200 iters", model="llama3_8b", n_blocks=32, iters=200,
+        scheme=dict(scheme="W4A16"), spec=("int_sym", 4, 128), linears=_LLAMA_LIN,
+        workload="Llama-3-8B W4A16 sym g128 iters=%d nsamples=128 seqlen=2048 batch=8 on %dxB200"),
+    "w2asym_algext": dict(
+        metric="Llama-3-8B W2A16 asym g32 enable_alg_ext calib wall-clock (s) @1000 iters", model="llama3_8b", n_blocks=32,
+        iters=1000, scheme=dict(scheme="W2A16", group_size=32, sym=False, enable_alg_ext=True), spec=("int_asym", 2, 32),
+        linears=_LLAMA_LIN, workload="Llama-3-8B W2A16 asym g32 enable_alg_ext iters=%d nsamples=128 seqlen=2048 batch=8 on %dxB200"),
+    "qwen2_nvfp4": dict(
+        metric="Qwen2-7B NVFP4 (weight-only) calib wall-clock (s) @200 iters", model="qwen2_7b", n_blocks=28, iters=200,
+        scheme=dict(scheme="NVFP4", act_bits=16, act_data_type="float"), spec=("nv_fp4", 4, 16), linears=_QWEN_LIN,
+        workload="Qwen2-7B NVFP4 weight-only g16 iters=%d nsamples=128 seqlen=2048 batch=8 on %dxB200"),
+}
+MODELS = {
+    "llama3_8b": ("LlamaConfig", "LlamaForCausalLM", dict(hidden_size=4096, intermediate_size=14336, num_attention_heads=32,
+                                                         num_key_value_heads=8, vocab_size=128256, rope_theta=500000.0,
+                                                         rms_norm_eps=1e-5, max_position_embeddings=8192)),
+    "qwen2_7b": ("Qwen2Config", "Qwen2ForCausalLM", dict(hidden_size=3584, intermediate_size=18944, num_attention_heads=28,
+                                                        num_key_value_heads=4, vocab_size=152064, rope_theta=1000000.0,
+                                                        rms_norm_eps=1e-6, max_position_embeddings=32768)),
+}
+
+
+def flops_per_step(cfg, iters):
+    """linear-layer FLOPs of one step (one block): `iters` iterations (3 GEMMs per linear, q/k/v need no
+    grad-in) + 2 full-set forwards."""
+    p_block = sum(n * k for _, n, k, _ in cfg["linears"])
+    p_nodx = sum(n * k for _, n, k, dx in cfg["linears"] if not dx)
+    return iters * (BATCH * SEQLEN) * (6 * p_block - 2 * p_nodx) + 2 * 2 * (NSAMPLES * SEQLEN) * p_block
 
 
 def peaks():
+    """MEASURED_PEAKS.json (driver-written): `bf16_tflops` = burst (a kernel timed alone), `bf16_tflops_sustained` = inside
+    a long step; fallback = B200_PROFILING.md."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "hbm_gbs": d.get("hbm_gbs"),
-                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained)"}
-    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"burst": d.get("bf16_tflops"), "sustained": d.get("bf16_tflops_sustained", d.get("bf16_tflops")),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "MEASURED_PEAKS.json"}
+    return {"burst": 1650.0, "sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler(threading.Thread):
@@ -113,21 +153,24 @@ class _Tok:
         return None
 
 
-def build_llama(n_layers: int, device, seed: int = 0):
-    """Random-init Llama-3-8B-shaped model with `n_layers` blocks, bf16, in PINNED host memory.  Initialised on the
-    GPU (fast) with HF's default init, then moved to the host: the public API receives a host model."""
-    from transformers import LlamaConfig, LlamaForCausalLM
+def build_model(name: str, n_layers: int, device, seed: int = 0):
+    """Random-init model of the named architecture with `n_layers` blocks, bf16, in PINNED host memory.  Initialised on
+    the GPU (fast) with HF's default init, then moved to the host: the public API receives a host model."""
+    import transformers
 
-    cfg = LlamaConfig(num_hidden_layers=n_layers, tie_word_embeddings=False, **LLAMA3_8B)
+    cfg_cls, model_cls, kw = MODELS[name]
+    cfg = getattr(transformers, cfg_cls)(num_hidden_layers=n_layers, tie_word_embeddings=False, **kw)
     cfg._attn_implementation = "sdpa"
     torch.manual_seed(seed)
     with torch.device("meta"):
-        model = LlamaForCausalLM(cfg)
+        model = getattr(transformers, model_cls)(cfg)
     model = model.to_empty(device=device).to(torch.bfloat16)
     g = torch.Generator(device=device).manual_seed(seed)
-    for name, p in model.named_parameters():
+    for pname, p in model.named_parameters():
         if p.dim() >= 2:
             p.data.normal_(0.0, cfg.initializer_range, generator=g)
+        elif pname.endswith("bias"):
+            p.data.zero_()
         else:
             p.data.fill_(1.0)
     # rotary inv_freq is a non-persistent buffer lost by to_empty(): rebuild it
@@ -142,9 +185,25 @@ def build_llama(n_layers: int, device, seed: int = 0):
     return model.eval()
 
 
+def build_llama(n_layers: int, device, seed: int = 0):
+    return build_model("llama3_8b", n_layers, device, seed)
+
+
+def line_config(cfg, iters, world, n_measured):
+    """The `config` object: identical for our arm and the reference arm (same workload)."""
+    return {"workload": cfg["workload"] % (iters, world),
+            "step": "one decoder block through the tuning span (ref fwd, %d sign-SGD iters, q fwd, unwrap, pack)" % iters,
+            "value_is": "ms_per_step x %d blocks (identical shapes)%s" % (cfg["n_blocks"], "" if n_measured != cfg["n_blocks"] else "; measured over all"),
+            "parallelism": "dp%d (calibration samples sharded; per layer: reduce-scatter of the bf16 dWq, row-sharded fused update, "
+                           "all-gather of the next fake-quant weight, overlapped with the backward)" % world,
+            "l2": "inputs larger than L2 (per-iteration working set 3.4 GB >> 126 MB)"}
+
+
 def run_ours(args):
     import torch.distributed as dist
 
+    cfg = CONFIGS[args.config]
+    iters = args.iters if args.iters else cfg["iters"]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -155,14 +214,16 @@ def run_ours(args):
     from auto_round_b200 import AutoRound, ops
 
     W, K = args.warmup, args.steps
-    model = build_llama(W + K, dev)
-    tokens = torch.randint(0, LLAMA3_8B["vocab_size"], (NSAMPLES, SEQLEN), generator=torch.Generator().manual_seed(1))
+    model = build_model(cfg["model"], W + K, dev)
+    orig_block0 = copy.deepcopy(model.model.layers[0]) if (world == 1 and not args.no_mse_check) else None
+    vocab = MODELS[cfg["model"]][2]["vocab_size"]
+    tokens = torch.randint(0, vocab, (NSAMPLES, SEQLEN), generator=torch.Generator().manual_seed(1))
     dataset = [tokens[i:i + BATCH] for i in range(0, NSAMPLES, BATCH)]
-    ar = AutoRound(model, tokenizer=_Tok(), scheme="W4A16", iters=args.iters, nsamples=NSAMPLES, seqlen=SEQLEN,
-                   batch_size=BATCH, dataset=dataset, device_map=local, seed=42)
+    ar = AutoRound(model, tokenizer=_Tok(), iters=iters, nsamples=NSAMPLES, seqlen=SEQLEN, batch_size=BATCH, dataset=dataset,
+                   device_map=local, seed=42, **cfg["scheme"])
     ar._pack_on_the_fly = True
 
-    ev = {"start": None, "end": None, "segs": []}
+    ev = {"segs": []}
     clocks = ClockSampler(local)
     launches0 = [0]
 
@@ -200,62 +261,91 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms, comp_ms = t.tolist()
 
-    dp_probe = collective_probe(dev, world) if world > 1 else None
+    dp_probe = collective_probe(dev, world, cfg) if world > 1 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pk = peaks()
+    nb = cfg["n_blocks"]
     ms_per_step = comp_ms / K
-    value_s = ms_per_step * N_BLOCKS_FULL / 1e3
-    e2e_s = (e2e_ms / K) * N_BLOCKS_FULL / 1e3
-    flops_step = FLOPS_PER_STEP * (args.iters / ITERS) if args.iters != ITERS else FLOPS_PER_STEP
-    roof = gemm_roofline(dev, pk)
-    h2d = (P_BLOCK + 2 * LLAMA3_8B["hidden_size"]) * 2              # bf16 linears + the two RMSNorm weights
-    d2h = int(P_BLOCK * 0.5 + (P_BLOCK // 128) * (2 + 0.5) + 4096 * 4 * 7)
+    value_s = ms_per_step * nb / 1e3
+    e2e_s = (e2e_ms / K) * nb / 1e3
+    flops_step = flops_per_step(cfg, iters)
+    p_block = sum(n * k for _, n, k, _ in cfg["linears"])
+    hidden = MODELS[cfg["model"]][2]["hidden_size"]
+    h2d = (p_block + 2 * hidden) * 2                                # bf16 linears + the two RMSNorm weights
+    bits, g = cfg["spec"][1], cfg["spec"][2]
+    d2h = int(p_block * bits / 8 + (p_block // g) * (2 + bits / 8) + hidden * 4 * 7)
+    tune_ms = sum(r["phases_ms"]["tune_ms"] for r in ar.block_results[W:]) / K
+    conf = line_config(cfg, iters, world, K)
+    conf["step_tflops_per_gpu"] = round(flops_step / (ms_per_step / 1e3) / 1e12 / world, 1)
+    mses = [r.get("block_mse") for r in ar.block_results[W:] if r.get("block_mse") is not None]
     line = {
-        "metric": "Llama-3-8B W4A16 calib wall-clock (s) @200 iters", "value": round(value_s, 3), "unit": "s",
+        "metric": cfg["metric"], "value": round(value_s, 3), "unit": "s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_per_step, 2), "higher_is_better": False,
-        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "Llama-3-8B W4A16 sym g128 iters=%d nsamples=128 seqlen=2048 batch=8 on %dxB200" % (args.iters, world),
-                   "step": "one decoder block through the tuning span (ref fwd, %d sign-SGD iters, q fwd, unwrap, int4 pack)" % args.iters,
-                   "value_is": "ms_per_step x 32 blocks (identical shapes)%s" % ("" if K != 32 else "; measured over all 32"),
-                   "parallelism": "dp%d (calibration samples sharded, 1 all-reduce of pre-sign grads per iteration)" % world,
-                   "l2": "inputs larger than L2 (per-iteration working set 3.4 GB >> 126 MB)",
-                   "step_tflops_per_gpu": round(flops_step / (ms_per_step / 1e3) / 1e12 / world, 1)},
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": conf,
         "e2e": {"value": round(e2e_s, 3), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
-        "roofline": roof,
-        "step_fraction_of_gemm_roofline": round((flops_step / world / (pk["bf16_tflops"] * 1e12)) / (ms_per_step / 1e3), 4),
+        "step_fraction_of_gemm_roofline": round((flops_step / world / (pk["sustained"] * 1e12)) / (ms_per_step / 1e3), 4),
         "phases_ms_per_step": {k: round(sum(r["phases_ms"][k] for r in ar.block_results[W:]) / K, 1)
                                for k in ar.block_results[W]["phases_ms"]},
+        "ms_per_iteration": round(tune_ms / iters, 3),
         "cuda_graph": bool(ar.block_results[W].get("cuda_graph")),
-        "losses": {"block0_iter0": ar.block_results[W]["init_loss"], "block0_best": ar.block_results[W]["best_loss"],
-                   "block0_best_iter": ar.block_results[W]["best_iter"]},
+        "losses": {"block0_iter0": ar.block_results[0]["init_loss"], "block0_best": ar.block_results[0]["best_loss"],
+                   "block0_best_iter": ar.block_results[0]["best_iter"]},
+        "block_output_mse": {"timed_blocks": mses, "what": "mean over valid tokens of (tuned block - FP block)^2 on all 128 samples"},
     }
     if dp_probe is not None:
         line["dp_probe"] = dp_probe
-    if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget)
+    if world == 1:
+        roof = gemm_roofline(dev, pk, cfg)
+        try:
+            roof["in_context"] = iteration_timeline(dev, pk, cfg, args.config)
+        except Exception as e:  # noqa: BLE001 -- a diagnostic, never the value
+            roof["in_context"] = {"error": repr(e)[:200]}
+        line["roofline"] = roof
+        if orig_block0 is not None:
+            try:
+                line["per_block_mse_vs_ref"] = mse_vs_reference(ar, model, orig_block0, cfg, iters, dev, line)
+            except Exception as e:  # noqa: BLE001
+                line["per_block_mse_vs_ref"] = {"error": repr(e)[:300]}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cfg, steps=3, warmup=1, budget_s=args.cpu_budget)
+    else:
+        line["roofline"] = {"bound": "tensor", "note": "measured at N=1 (same kernels); see the N=1 line"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def collective_probe(dev, world):
-    """The two data-path collectives of the DP run timed alone (CUDA events, after the timed region): the per-iteration
-    all-reduce of the bf16 pre-sign rounding gradients (one block: 218 M values) and the per-block all-gather that rebuilds
-    the 128 x 2048 x 4096 bf16 block outputs.  Diagnostic only."""
+def collective_probe(dev, world, cfg):
+    """The data-path collectives of the DP run timed alone (CUDA events, after the timed region): per iteration one
+    reduce-scatter of the bf16 dWq and one all-gather of the bf16 Wq per layer (summed over the block's layers here), and
+    per block the all-gather that rebuilds the 128 x 2048 x hidden bf16 block outputs.  Diagnostic only."""
     import torch.distributed as dist
 
-    g = torch.zeros(P_BLOCK, dtype=torch.bfloat16, device=dev)
+    hidden = MODELS[cfg["model"]][2]["hidden_size"]
+    lay = [(n, k) for _, n, k, _ in cfg["linears"] if n % world == 0]
+    full = [torch.zeros(n, k, dtype=torch.bfloat16, device=dev) for n, k in lay]
+    shard = [torch.zeros(n // world, k, dtype=torch.bfloat16, device=dev) for n, k in lay]
     per = NSAMPLES // world
-    loc = torch.zeros(per, SEQLEN, LLAMA3_8B["hidden_size"], dtype=torch.bfloat16, device=dev)
-    full = torch.empty(per * world, SEQLEN, LLAMA3_8B["hidden_size"], dtype=torch.bfloat16, device=dev)
+    loc = torch.zeros(per, SEQLEN, hidden, dtype=torch.bfloat16, device=dev)
+    outs = torch.empty(per * world, SEQLEN, hidden, dtype=torch.bfloat16, device=dev)
+    nbytes = sum(t.numel() * 2 for t in full)
+
+    def rs():
+        for f, s in zip(full, shard):
+            dist.reduce_scatter_tensor(s, f)
+
+    def ag():
+        for f, s in zip(full, shard):
+            dist.all_gather_into_tensor(f, s)
+
     out = {}
-    for name, fn, n, nbytes in (("allreduce_gradv", lambda: dist.all_reduce(g), 10, g.numel() * 2),
-                                ("allgather_outputs", lambda: dist.all_gather_into_tensor(full, loc), 4, full.numel() * 2)):
+    for name, fn, n, nb in (("reduce_scatter_dwq_all_layers", rs, 10, nbytes), ("all_gather_wq_all_layers", ag, 10, nbytes),
+                            ("allgather_outputs", lambda: dist.all_gather_into_tensor(outs, loc), 4, outs.numel() * 2)):
         fn()
         torch.cuda.synchronize()
         dist.barrier()
@@ -266,40 +356,37 @@ def collective_probe(dev, world):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
-        out[name] = {"ms": round(ms, 3), "bytes": int(nbytes), "GBps_algo": round(nbytes / ms / 1e6, 1)}
+        out[name] = {"ms": round(ms, 3), "bytes": int(nb), "GBps_algo": round(nb / ms / 1e6, 1)}
     return out
 
 
-def gemm_roofline(dev, pk):
-    """Replay the GEMM launch mix of ONE sign-SGD iteration of a Llama-3-8B block (7 forward, 4 grad-input and
-    7 fused grad-weight launches at T = 16384 tokens) back to back and time it with CUDA events on the launch stream."""
+def _gemm_mix(dev, cfg):
     from auto_round_b200 import ops
 
     T = BATCH * SEQLEN
-    shapes = [("q", 4096, 4096, False), ("k", 1024, 4096, False), ("v", 1024, 4096, False), ("o", 4096, 4096, True),
-              ("gate", 14336, 4096, True), ("up", 14336, 4096, True), ("down", 4096, 14336, True)]
-    bufs = {}
-    flops = 0
-    nlaunch = 0
-    for name, n, k, dx in shapes:
-        spec = ops.make_spec("int_sym", 4, 128, n, k)
+    bufs, flops, nlaunch = {}, 0, 0
+    for name, n, k, dx in cfg["linears"]:
         w = (torch.randn(n, k, device=dev) * 0.02).bfloat16()
-        bufs[name] = dict(spec=spec, w=w, x=torch.randn(T, k, device=dev).bfloat16(), dy=torch.randn(T, n, device=dev).bfloat16(),
-                          v=torch.zeros(n, k, device=dev), mn=torch.ones(spec.groups, device=dev), mx=torch.ones(spec.groups, device=dev),
-                          mm=ops.group_minmax(spec, w), dv=torch.empty(n, k, device=dev), dmn=torch.empty(spec.groups, device=dev),
-                          dmx=torch.empty(spec.groups, device=dev), y=torch.empty(T, n, device=dev, dtype=torch.bfloat16),
+        bufs[name] = dict(w=w, x=torch.randn(T, k, device=dev).bfloat16(), dy=torch.randn(T, n, device=dev).bfloat16(),
+                          gq=torch.empty(n, k, device=dev, dtype=torch.bfloat16), y=torch.empty(T, n, device=dev, dtype=torch.bfloat16),
                           dxo=torch.empty(T, k, device=dev, dtype=torch.bfloat16), dx=dx)
         flops += 2 * T * n * k * (3 if dx else 2)
         nlaunch += 3 if dx else 2
 
     def one_iter():
         for b in bufs.values():
-            ops.gemm(b["x"], b["w"], out=b["y"])
+            ops.gemm(b["x"], b["w"], out=b["y"])                                         # forward  Y = X Wq^T
             if b["dx"]:
-                ops.gemm(b["dy"], b["w"], False, True, out=b["dxo"])
-            ops.fq_linear_bwd_dw(b["spec"], b["dy"], b["x"], b["w"], b["v"], b["mn"], b["mx"], b["mm"][0], b["mm"][1], None,
-                                 b["dv"], b["dmn"], b["dmx"])
+                ops.gemm(b["dy"], b["w"], False, True, out=b["dxo"])                     # grad-in  dX = dY Wq
+            ops.gemm(b["dy"], b["x"], True, True, out=b["gq"])                           # grad-w   dWq = dY^T X (bf16)
+    return one_iter, flops, nlaunch
 
+
+def gemm_roofline(dev, pk, cfg):
+    """Replay the GEMM launch mix of ONE sign-SGD iteration (7 forward, 4 grad-input, 7 grad-weight launches at
+    T = 16384 tokens) back to back and time it with CUDA events on the launch stream.  The replay is ~0.2 s of isolated
+    launches, so the roofline denominator is the BURST cuBLAS peak; the in-context figure uses the sustained one."""
+    one_iter, flops, nlaunch = _gemm_mix(dev, cfg)
     for _ in range(3):
         one_iter()
     torch.cuda.synchronize()
@@ -312,25 +399,184 @@ def gemm_roofline(dev, pk):
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / reps
     achieved = flops / (ms / 1e3) / 1e12
-    return {"bound": "tensor", "kernel": "ar::gemm_kernel (tcgen05, 128x256x64 tiles; fwd / grad-in / fused grad-w)",
-            "achieved": round(achieved, 1), "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops"], 4),
-            "peak_source": pk["source"], "traffic": None, "flops_per_launch": flops // nlaunch,
+    traffic, tsrc = None, None
+    tp = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+    if os.path.exists(tp):
+        td = json.load(open(tp))
+        traffic, tsrc = td.get("dram_bytes_per_launch_avg"), td.get("source")
+    return {"bound": "tensor", "kernel": "ar::gemm_kernel (tcgen05 cta_group::2, 256x256x64 tiles, dynamic tile scheduler; fwd / grad-in / grad-w)",
+            "achieved": round(achieved, 1), "peak": pk["burst"], "unit": "TFLOP/s", "frac": round(achieved / pk["burst"], 4),
+            "peak_source": pk["source"] + " bf16_tflops (burst: the replay is an isolated ~0.2 s run)",
+            "traffic": traffic, "traffic_source": tsrc, "flops_per_launch": flops // nlaunch,
+            "algorithmic_bytes_per_launch": int(sum(2 * (BATCH * SEQLEN * (n + k) + n * k) * (3 if dx else 2)
+                                                    for _, n, k, dx in cfg["linears"]) / nlaunch),
             "avg_launch_ms": round(ms / nlaunch, 4), "launches_per_iteration": nlaunch,
-            "how": "18 GEMM launches of one iteration replayed x10 after 3 warm-ups; operands 3.4 GB >> L2",
-            # dram read+write per launch from the one `ncu --set full` capture on file (gate/up_proj shape, 1.92e12 FLOP):
-            # the mix above averages over 7 layer shapes, for which no per-launch capture exists, hence traffic = null
-            "traffic_ncu_gate_proj_bytes": {"fwd": 1668550800, "grad_in": 2475847704, "grad_w_fused": 3952551056,
-                                            "algorithmic": {"fwd": 721420288, "grad_in": 721420288, "grad_w_fused": 1191182336},
-                                            "source": "profiles/r01_ncu_prof_gemm2.md"}}
+            "how": "%d GEMM launches of one iteration replayed x10 after 3 warm-ups; operands 3.4 GB >> L2" % nlaunch}
 
 
-def cpu_baseline(budget_s: float = 25.0, threads=None):
-    """The reference's algorithm on the host cores (oracle/signround.py: torch-CPU restatement pinned bit-exact to
-    the reference): sign-SGD iterations of ONE full-shape Llama-3-8B block on a bounded sample (1 sample of 2048
-    tokens per iteration instead of 8), extrapolated to the metric's unit."""
-    from transformers import LlamaConfig
-    from transformers.models.llama.modeling_llama import LlamaDecoderLayer, LlamaRotaryEmbedding
+def iteration_timeline(dev, pk, cfg, cfg_name):
+    """Kernel timeline of ONE steady-state iteration inside the CUDA-graph replay of a real block (CUPTI through
+    torch.profiler; 14 iterations, the 6th is read): where the iteration's time goes and what the GEMMs achieve IN CONTEXT
+    (back to back with everything else, at the sustained clock).  A diagnostic taken under the profiler -- never a value."""
+    from torch.profiler import ProfilerActivity, profile
 
+    from auto_round_b200.quantizer import SignRoundQuantizer
+    from auto_round_b200.schemes import parse_scheme
+
+    model = build_model(cfg["model"], 1, dev)
+    blk = model.model.layers[0].to(dev)
+    for p in blk.parameters():
+        p.requires_grad_(False)
+    hidden = MODELS[cfg["model"]][2]["hidden_size"]
+    ns = 16
+    torch.manual_seed(0)
+    xs = [torch.randn(1, SEQLEN, hidden, device=dev).bfloat16() * 0.05 for _ in range(ns)]
+    pos = torch.arange(SEQLEN, device=dev).unsqueeze(0)
+    cos, sin = model.model.rotary_emb.to(dev)(xs[0], pos)
+    others = {"position_embeddings": [(cos.bfloat16(), sin.bfloat16())], "position_ids": [pos], "attention_mask": None}
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        refs = [blk(x, position_embeddings=others["position_embeddings"][0]) for x in xs]
+    refs = [(r[0] if isinstance(r, (tuple, list)) else r).reshape(1, SEQLEN, hidden) for r in refs]
+    sk = dict(cfg["scheme"])
+    alg_ext = bool(sk.pop("enable_alg_ext", False))
+    scheme = parse_scheme(sk.pop("scheme"), sk)
+    q = SignRoundQuantizer(scheme, iters=14, batch_size=BATCH, enable_alg_ext=alg_ext)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        q.quantize_block(blk, xs, others, refs, None, None, input_ids=None)
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    idx = [i for i, e in enumerate(evs) if "iter_advance" in e.name]
+    if len(idx) < 8:
+        return {"error": "timeline too short"}
+    it = evs[idx[5] + 1:idx[6] + 1]
+    span = (it[-1].time_range.end - it[0].time_range.start) / 1e3
+    agg = {}
+    for e in it:
+        name = e.name
+        key = ("ar::gemm_kernel" if "gemm_kernel" in name else "cudnn sdpa" if ("sdpa" in name or "cudnn" in name or "fmha" in name)
+               else "ar::fq_update_kernel" if "fq_update" in name else "ar::swiglu" if "swiglu" in name
+               else "aten elementwise" if "at::native" in name else "ar:: other" if name.startswith(("ar::", "void ar::")) else "other")
+        c, t_ = agg.get(key, (0, 0.0))
+        agg[key] = (c + 1, t_ + (e.time_range.end - e.time_range.start) / 1e3)
+    flops_iter = (BATCH * SEQLEN) * (6 * sum(n * k for _, n, k, _ in cfg["linears"]) - 2 * sum(n * k for _, n, k, dx in cfg["linears"] if not dx))
+    gemm_ms = agg.get("ar::gemm_kernel", (0, 0.0))[1]
+    return {"iteration_ms": round(span, 3), "kernels": len(it), "gemm_ms": round(gemm_ms, 3),
+            "gemm_tflops_in_context": round(flops_iter / (gemm_ms / 1e3) / 1e12, 1) if gemm_ms else None,
+            "frac_of_sustained_peak": round(flops_iter / (gemm_ms / 1e3) / 1e12 / pk["sustained"], 4) if gemm_ms else None,
+            "by_kernel_ms": {k: [c, round(t_, 3)] for k, (c, t_) in sorted(agg.items(), key=lambda kv: -kv[1][1])},
+            "how": "torch.profiler (CUPTI) over a 14-iteration quantize_block of one real block, 6th graph-replayed iteration"}
+
+
+def _block_inputs_for_check(ar, model, dev):
+    """Inputs of block 0 exactly as the tuned run cached them (embedding of the synthetic tokens)."""
+    hidden, others, ids = ar.cache_block_inputs(model.model.layers[0])
+    return hidden, others, ids
+
+
+def mse_vs_reference(ar, model, orig_block0, cfg, iters, dev, line):
+    """BASELINE.json's "per-block MSE vs ref": block 0 (FP inputs = embeddings, so both runs see identical inputs) tuned
+    (a) by this engine inside the timed run, (b) by the reference's algorithm -- oracle/signround.py BlockTuner, torch eager
+    with autograd on the same GPU, the SAME batch sequence -- and the final output MSE of each against the FP block over
+    all 128 samples (valid tokens).  Also yields the reference's eager per-iteration time on this GPU."""
+    from oracle import signround as S
+
+    blocks = ar._blocks
+    hidden, others, ids = ar.cache_block_inputs(blocks[0])
+    blocks[0].to("cpu")
+    masks = [(i != -100).to(torch.long).to(dev) for i in ids]
+    fp = copy.deepcopy(orig_block0).to(dev)
+    okw = {k: v for k, v in others.items()}
+
+    def fwd_all(blk):
+        outs = []
+        with torch.no_grad():
+            for i in range(0, len(hidden), BATCH):
+                x, sel = S.select_batch(hidden, okw, list(range(i, min(i + BATCH, len(hidden)))))
+                outs.extend(torch.split(S.block_forward(blk, x, sel), 1, dim=0))
+        return outs
+
+    def mse(outs, refs):
+        tot = torch.zeros((), dtype=torch.float64, device=dev)
+        cnt = 0
+        for o, r, m in zip(outs, refs, masks):
+            d = (o.float() - r.float()) * m.reshape(1, -1, 1)
+            tot += (d.double() ** 2).sum()
+            cnt += int(m.sum()) * o.shape[-1]
+        return float(tot) / cnt
+
+    refs = fwd_all(fp)
+    sk = dict(cfg["scheme"])
+    alg_ext = bool(sk.pop("enable_alg_ext", False))
+    name, bits, g = cfg["spec"]
+    osc = S.LayerScheme(bits, g, name != "int_asym", {"int_sym": "int", "int_asym": "int", "mx_fp4": "mx_fp", "nv_fp4": "nv_fp"}[name])
+    # RTN (iteration-0 parameters): the floor both tuners start from
+    rtn = copy.deepcopy(orig_block0).to(dev)
+    wr = S.wrap_block(rtn, lambda n, m: osc)
+    S.unwrap_block(rtn, wr, {})
+    mse_rtn = mse(fwd_all(rtn), refs)
+    del rtn, wr
+    # the reference's algorithm, eager on this GPU, same batches as block 0 of the timed run
+    oblk = copy.deepcopy(orig_block0).to(dev)
+    batches = ar.block_results[0]["batches"]
+    nv = None
+    if name == "nv_fp4":
+        from oracle import qdq as Q
+        nv = {n: Q.nv_global_scale(m.weight.data) for n, m in oblk.named_modules() if type(m) is torch.nn.Linear}
+        for grp in (("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj"), ("mlp.gate_proj", "mlp.up_proj")):
+            shared = torch.stack([nv[n] for n in grp]).min()
+            for n in grp:
+                nv[n] = shared
+    tuner = S.BlockTuner(oblk, hidden, okw, refs, lambda n, m: osc, iters=iters, batch_size=BATCH, token_masks=masks,
+                         sampler=S.ReplaySampler(batches), nv_global_scales=nv, alg_ext=alg_ext)
+    times = []
+    for it in range(iters):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tuner.step(it)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    ores = tuner.finish()
+    mse_ref = mse(fwd_all(oblk), refs)
+    ours = ar.block_results[0].get("block_mse")
+    steady = sorted(times[3:])
+    eager_ms = 1e3 * steady[len(steady) // 2]
+    line["gpu_eager_baseline"] = {
+        "what": "the reference's algorithm as torch eager + autograd on the same B200 (oracle/signround.py on cuda: ATen fake-quant "
+                "graph, cuBLAS GEMMs, SDPA) -- the reference's GPU path without torch.compile",
+        "ms_per_iteration": round(eager_ms, 2), "ours_ms_per_iteration": line["ms_per_iteration"],
+        "speedup_per_iteration": round(eager_ms / line["ms_per_iteration"], 2),
+        "loop_only_extrapolation_s": round(eager_ms * iters * cfg["n_blocks"] / 1e3, 1), "iterations_timed": len(steady)}
+    return {"block": 0, "ours": ours, "reference_algorithm": mse_ref, "ratio": (ours / mse_ref) if (ours and mse_ref) else None,
+            "rtn": mse_rtn, "ours_init_loss_x_tokens": ar.block_results[0]["init_loss"], "ref_iter0_loss": ores.losses[0],
+            "ours_iter0_loss": ar.block_results[0]["losses"][0], "ref_best_iter": ores.best_iter,
+            "ours_best_iter": ar.block_results[0]["best_iter"],
+            "what": "final output MSE vs the FP block over all 128 samples (valid tokens); same inputs, same batch sequence"}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm (CPU)
+def _cpu_block(cfg):
+    import transformers
+
+    cfg_cls, _, kw = MODELS[cfg["model"]]
+    c = getattr(transformers, cfg_cls)(num_hidden_layers=1, **kw)
+    c._attn_implementation = "sdpa"
+    torch.manual_seed(0)
+    mod = __import__("transformers.models.%s.modeling_%s" % (("llama", "llama") if cfg["model"].startswith("llama") else ("qwen2", "qwen2")),
+                     fromlist=["x"])
+    layer_cls = getattr(mod, "LlamaDecoderLayer" if cfg["model"].startswith("llama") else "Qwen2DecoderLayer")
+    rot_cls = getattr(mod, "LlamaRotaryEmbedding" if cfg["model"].startswith("llama") else "Qwen2RotaryEmbedding")
+    return c, layer_cls(c, 0).to(torch.bfloat16).eval(), rot_cls(c)
+
+
+def cpu_steps(cfg, steps, warmup, budget_s, threads=None):
+    """The reference's algorithm on the host cores: oracle/signround.py BlockTuner (CPU restatement pinned bit-exact to the
+    reference) on ONE full-shape block, wrapper built once.  A STEP is one whole sign-SGD iteration (forward, loss, autograd
+    backward through the fake-quant graph, sign-SGD update of every layer) on a bounded token sample: steps alternate
+    between T_small and T_large = 4 T_small tokens, which separates the weight-sized cost `a` (fake-quant forward/backward and
+    update of 218 M weights: independent of the batch) from the per-token cost `b` (GEMMs, attention): t(T) = a + b T.
+    The metric is then extrapolated: blocks x iters x (a + b x 16384 tokens).  Full-set forwards and pack are not included."""
     from oracle import signround as S
 
     if threads is None:
@@ -342,53 +588,75 @@ def cpu_baseline(budget_s: float = 25.0, threads=None):
             threads = os.cpu_count() or 1
     torch.set_num_threads(max(1, int(threads)))
     cores = torch.get_num_threads()
-    cfg = LlamaConfig(num_hidden_layers=1, **LLAMA3_8B)
-    cfg._attn_implementation = "sdpa"
-    torch.manual_seed(0)
-    blk = LlamaDecoderLayer(cfg, 0).to(torch.bfloat16).eval()
-    nsamp, seq = 2, SEQLEN
-    xs = [torch.randn(1, seq, cfg.hidden_size).to(torch.bfloat16) * 0.02 for _ in range(nsamp)]
-    pos = torch.arange(seq).unsqueeze(0)
-    rot = LlamaRotaryEmbedding(cfg)
-    cos, sin = rot(xs[0], pos)
-    others = {"position_embeddings": [(cos.to(torch.bfloat16), sin.to(torch.bfloat16))], "position_ids": [pos],
-              "attention_mask": None}
+    c, blk, rot = _cpu_block(cfg)
+    name, bits, g = cfg["spec"]
+    osc = S.LayerScheme(bits, g, name != "int_asym", {"int_sym": "int", "int_asym": "int", "mx_fp4": "mx_fp", "nv_fp4": "nv_fp"}[name])
+    t_small = 64
+    sizes = [t_small, 4 * t_small]
+    n_total = steps + warmup
+    xs, refs, others_by = [], [], {}
+    for i in range(n_total):
+        T = sizes[i % 2]
+        xs.append(torch.randn(1, T, c.hidden_size).to(torch.bfloat16) * 0.02)
+    inputs, fp_out, pos_emb = [], [], []
     with torch.no_grad():
-        refs = [S.block_forward(blk, x, {"position_embeddings": others["position_embeddings"][0], "position_ids": pos}) for x in xs]
-    sc = S.LayerScheme(4, 128, True, "int")
-    t0 = time.time()
-    iters_done = 0
-    # time whole iterations until the budget is spent (the first includes wrapper construction, like the reference)
-    n_it = 1
-    res = None
-    while True:
-        t1 = time.time()
-        import copy
-        b2 = copy.deepcopy(blk)
-        res = S.tune_block(b2, xs, others, refs, lambda n, m: sc, iters=n_it, batch_size=1, lr=1.0 / ITERS)
-        dt = time.time() - t1
-        iters_done += n_it
-        if time.time() - t0 + dt > budget_s or iters_done >= 3:
+        for x in xs:
+            pos = torch.arange(x.shape[1]).unsqueeze(0)
+            cos, sin = rot(x, pos)
+            pe = (cos.to(torch.bfloat16), sin.to(torch.bfloat16))
+            pos_emb.append(pe)
+            fp_out.append(S.block_forward(blk, x, {"position_embeddings": pe, "position_ids": pos}))
+    # per-sample position embeddings differ in length: hand them over as per-sample lists through a tiny sampler-driven shim
+    tuner = S.BlockTuner(blk, xs, {"attention_mask": None}, fp_out, lambda n, m: osc, iters=max(cfg["iters"], n_total), batch_size=1,
+                         lr=1.0 / cfg["iters"], sampler=S.ReplaySampler([[i] for i in range(n_total)]))
+    times, t_begin = [], time.time()
+    for i in range(n_total):
+        pos = torch.arange(xs[i].shape[1]).unsqueeze(0)
+        tuner.others = {"attention_mask": None, "position_embeddings": [pos_emb[i]], "position_ids": [pos]}
+        t0 = time.perf_counter()
+        tuner.step(i)
+        times.append((xs[i].shape[1], time.perf_counter() - t0))
+        if i >= warmup + 1 and (time.time() - t_begin) > budget_s and len(times) - warmup >= 2:
             break
-    per_iter_1sample = dt / n_it
-    per_iter = per_iter_1sample * BATCH            # batch 8 x 2048 tokens; GEMM-bound, linear in tokens
-    total_s = per_iter * ITERS * N_BLOCKS_FULL
-    return {"value": round(total_s, 1), "unit": "s", "cores": cores, "kind": "port",
-            "sample": "oracle/signround.py (CPU restatement, pinned bit-exact to the reference) on ONE full-shape Llama-3-8B "
-                      "block: %.1f s per sign-SGD iteration at 1x2048 tokens, x8 (batch) x200 (iters) x32 (blocks); "
-                      "EXTRAPOLATED, full-set forwards and pack not included" % per_iter_1sample}
+    timed = times[warmup:]
+    sm = [t for T, t in timed if T == sizes[0]]
+    lg = [t for T, t in timed if T == sizes[1]]
+    if sm and lg:
+        ts, tl = sum(sm) / len(sm), sum(lg) / len(lg)
+        b = max((tl - ts) / (sizes[1] - sizes[0]), 0.0)
+        a = max(ts - b * sizes[0], 0.0)
+    else:                                   # a single size was timed: everything attributed to the tokens (upper bound)
+        allt = sm or lg
+        T0 = sizes[0] if sm else sizes[1]
+        a, b = 0.0, (sum(allt) / len(allt)) / T0
+    per_iter = a + b * (BATCH * SEQLEN)
+    total_s = per_iter * cfg["iters"] * cfg["n_blocks"]
+    step_ms = 1e3 * sum(t for _, t in timed) / max(len(timed), 1)
+    return {"value": round(total_s, 1), "unit": "s", "cores": cores, "kind": "port", "ms_per_step": round(step_ms, 1), "steps_timed": len(timed),
+            "fit": {"weight_sized_s_per_iter": round(a, 3), "s_per_token_per_iter": round(b, 6), "s_per_full_iteration": round(per_iter, 2)},
+            "sample": "oracle/signround.py BlockTuner (CPU restatement pinned bit-exact to the reference; wrapper built once) on ONE "
+                      "full-shape block; each step = one whole sign-SGD iteration on %d or %d tokens (alternating); fit t = a + b T, "
+                      "extrapolated to 8x2048 tokens x %d iters x %d blocks; EXTRAPOLATED, full-set forwards and pack not included; "
+                      "nproc=%d" % (sizes[0], sizes[1], cfg["iters"], cfg["n_blocks"], cores)}
+
+
+def cpu_baseline(cfg, steps=3, warmup=1, budget_s=40.0):
+    return cpu_steps(cfg, steps, warmup, budget_s)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(budget_s=max(20.0, 30.0 * max(args.steps, 1)))
-    line = {"impl": "reference", "metric": "Llama-3-8B W4A16 calib wall-clock (s) @200 iters", "value": cb["value"], "unit": "s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(cb["value"] / N_BLOCKS_FULL * 1e3, 1),
+    cfg = CONFIGS[args.config]
+    iters = args.iters if args.iters else cfg["iters"]
+    cb = cpu_steps(cfg, max(args.steps, 2), max(args.warmup, 1), budget_s=150.0)
+    line = {"impl": "reference", "metric": cfg["metric"], "value": cb["value"], "unit": "s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "Llama-3-8B W4A16 sym g128 iters=200 nsamples=128 seqlen=2048 batch=8, reference CPU path "
-                                   "(the reference has no C/C++ on this path; its Python is restated in oracle/ and timed on the host cores)"},
+            "config": line_config(cfg, iters, args.gpus, args.steps),
+            "reference_note": "the reference has no C/C++ on this path; its Python is restated in oracle/ (pinned bit-exact) and timed on the "
+                              "host cores; ms_per_step is one bounded sample step, `value` the extrapolation described in cpu_baseline.sample",
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -400,9 +668,11 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--iters", type=int, default=ITERS, help="sign-SGD iterations per block (metric: 200)")
+    ap.add_argument("--config", default="llama3_8b_w4a16", choices=sorted(CONFIGS))
+    ap.add_argument("--iters", type=int, default=0, help="sign-SGD iterations per block (0: the config's own, metric: 200)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--no-mse-check", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=40.0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -82,10 +82,10 @@ class TunableLinear(nn.Module):
         groups, _, _ = Q.to_groups(w, scheme.group_size)
         self.wmin = torch.clamp(groups.min(1)[0], max=0)
         self.wmax = torch.clamp(groups.max(1)[0], min=0)
-        self.value = nn.Parameter(torch.zeros(groups.shape, dtype=torch.float32))
+        self.value = nn.Parameter(torch.zeros(groups.shape, dtype=torch.float32, device=w.device))
         nscale = groups.shape[0]
-        self.min_scale = nn.Parameter(torch.ones(nscale, dtype=torch.float32))
-        self.max_scale = nn.Parameter(torch.ones(nscale, dtype=torch.float32))
+        self.min_scale = nn.Parameter(torch.ones(nscale, dtype=torch.float32, device=w.device))
+        self.max_scale = nn.Parameter(torch.ones(nscale, dtype=torch.float32, device=w.device))
         self.q_scale_thresh = 1e-8 if scheme.scale_dtype == torch.float32 else 1e-5
         self.global_scale = None
         if scheme.data_type == "nv_fp":
@@ -234,7 +234,7 @@ def select_batch(inputs, others: dict, idx):
             vals = [val[i] for i in idx]
             sel[key] = vals[0] if len(vals) == 1 else torch.cat(vals, dim=0)
         elif isinstance(val, torch.Tensor):
-            sel[key] = torch.index_select(val, 0, torch.tensor(list(idx)))
+            sel[key] = torch.index_select(val, 0, torch.tensor(list(idx), device=val.device))
         else:
             sel[key] = val
     return x, sel
@@ -243,7 +243,7 @@ def select_batch(inputs, others: dict, idx):
 def block_forward(block, hidden, others: dict, amp=True, amp_dtype=torch.bfloat16):
     kw = dict(others)
     if amp:
-        with torch.autocast(device_type="cpu", dtype=amp_dtype):
+        with torch.autocast(device_type=hidden.device.type, dtype=amp_dtype):
             out = block(hidden, **kw)
     else:
         out = block(hidden, **kw)
@@ -266,54 +266,63 @@ class TuneResult:
     batches: list = field(default_factory=list)
 
 
-def tune_block(block, inputs, others, fp_outputs, scheme_of, iters=200, batch_size=8, lr=None, minmax_lr=None,
-               token_masks=None, enable_minmax_tuning=True, nv_global_scales=None, amp=True,
-               not_use_best_mse=False, sampler=None, alg_ext=False, imatrices=None, outlier_loss=None) -> TuneResult:
-    """quantize_block: `inputs`/`fp_outputs` are per-sample lists of [1,S,H]; `token_masks` per-sample [1,S]
-    long tensors (1 = valid) or None.  Mutates `block` in place (qdq weights + scale/zp attributes)."""
-    nsamples = len(inputs)
-    wrapped = wrap_block(block, scheme_of, nv_global_scales, alg_ext, imatrices)
-    if outlier_loss is None:   # sign_roundv2/quantizer.py:334-352: symmetric schemes with bits < 4 (act quant is out of scope)
-        outlier_loss = alg_ext and any(tl.init_scale is not None and tl.scheme.bits < 4 for tl in wrapped.values())
-    res = TuneResult()
-    if not wrapped:
-        return res
+class BlockTuner:
+    """quantize_block as a stepper: construction = wrapper_block + optimizer / scheduler / sampler set-up
+    (quantizer.py:311-436), `step(it)` = one iteration of the loop (quantizer.py:455-552), `finish()` = apply the best
+    parameters and unwrap.  `tune_block` below is the plain loop over it; the bench times `step` on the host cores (the
+    reference's CPU path) and on the GPU (the reference's eager ATen + cuBLAS path) without the set-up cost."""
 
-    def lr_for(bits):
-        if lr is not None:
-            return lr
-        return 2.0 / iters if (iters >= 1000 and bits <= 3) else 1.0 / iters
+    def __init__(self, block, inputs, others, fp_outputs, scheme_of, iters=200, batch_size=8, lr=None, minmax_lr=None,
+                 token_masks=None, enable_minmax_tuning=True, nv_global_scales=None, amp=True, not_use_best_mse=False,
+                 sampler=None, alg_ext=False, imatrices=None, outlier_loss=None):
+        self.block, self.inputs, self.others, self.fp_outputs = block, inputs, others, fp_outputs
+        self.iters, self.token_masks, self.amp, self.alg_ext = iters, token_masks, amp, alg_ext
+        self.not_use_best_mse = not_use_best_mse
+        nsamples = len(inputs)
+        self.wrapped = wrapped = wrap_block(block, scheme_of, nv_global_scales, alg_ext, imatrices)
+        if outlier_loss is None:   # sign_roundv2/quantizer.py:334-352: symmetric schemes with bits < 4 (act quant is out of scope)
+            outlier_loss = alg_ext and any(tl.init_scale is not None and tl.scheme.bits < 4 for tl in wrapped.values())
+        self.outlier_loss = outlier_loss
+        self.res = TuneResult()
+        if not wrapped:
+            return
 
-    # one lr tensor per param group, scaled by the same LinearLR factors (quantizer.py:374-429)
-    groups = []
-    for tl in wrapped.values():
-        base = lr_for(tl.scheme.bits)
-        groups.append(([tl.value], torch.tensor(float(base))))
-        if enable_minmax_tuning:
-            mm = [tl.max_scale] if tl.scheme.data_type != "int" else [tl.min_scale, tl.max_scale]
-            groups.append((mm, torch.tensor(float(minmax_lr if minmax_lr is not None else base))))
-    if not enable_minmax_tuning:
+        def lr_for(bits):
+            if lr is not None:
+                return lr
+            return 2.0 / iters if (iters >= 1000 and bits <= 3) else 1.0 / iters
+
+        # one lr tensor per param group, scaled by the same LinearLR factors (quantizer.py:374-429)
+        self.groups = groups = []
         for tl in wrapped.values():
-            tl.min_scale.requires_grad_(False)
-            tl.max_scale.requires_grad_(False)
+            base = lr_for(tl.scheme.bits)
+            groups.append(([tl.value], torch.tensor(float(base))))
+            if enable_minmax_tuning:
+                mm = [tl.max_scale] if tl.scheme.data_type != "int" else [tl.min_scale, tl.max_scale]
+                groups.append((mm, torch.tensor(float(minmax_lr if minmax_lr is not None else base))))
+        if not enable_minmax_tuning:
+            for tl in wrapped.values():
+                tl.min_scale.requires_grad_(False)
+                tl.max_scale.requires_grad_(False)
+        gbs = min(nsamples, batch_size)
+        self.sampler = sampler if sampler is not None else IndexSampler(nsamples, gbs)
+        self.best_loss = torch.finfo(torch.float).max
 
-    gbs = min(nsamples, batch_size)
-    sampler = sampler if sampler is not None else IndexSampler(nsamples, gbs)
-    best_loss = torch.finfo(torch.float).max
-    for it in range(iters):
-        idx = sampler.next_batch()
+    def step(self, it):
+        res, wrapped, token_masks = self.res, self.wrapped, self.token_masks
+        idx = self.sampler.next_batch()
         res.batches.append(list(idx))
         num_elm = 1
         mask = None
         if token_masks:
             num_elm = sum(int(torch.count_nonzero(token_masks[i]).item()) for i in idx)
             mask = torch.cat([token_masks[i] for i in idx], dim=0).unsqueeze(-1)
-        ref = torch.cat([fp_outputs[i] for i in idx], dim=0)
-        x, sel = select_batch(inputs, others, idx)
-        pred = block_forward(block, x, sel, amp)
-        if outlier_loss:
+        ref = torch.cat([self.fp_outputs[i] for i in idx], dim=0)
+        x, sel = select_batch(self.inputs, self.others, idx)
+        pred = block_forward(self.block, x, sel, self.amp)
+        if self.outlier_loss:
             loss = outlier_suppressed_loss(pred, ref, mask)
-        elif alg_ext:
+        elif self.alg_ext:
             # SignRoundV2Quantizer._get_loss falls back to super()._get_loss WITHOUT forwarding valid_token_mask
             # (sign_roundv2/quantizer.py:399): plain MSE over every token; num_elm below still counts valid tokens only
             loss = masked_mse(pred, ref, None)
@@ -323,28 +332,47 @@ def tune_block(block, inputs, others, fp_outputs, scheme_of, iters=200, batch_si
         total = loss.item() / num_elm
         (loss * 1000).backward()
         res.losses.append(total)
-        if total < best_loss:
-            best_loss = total
-            if not not_use_best_mse:
+        if total < self.best_loss:
+            self.best_loss = total
+            if not self.not_use_best_mse:
                 res.best_params = {n: {k: p.data.clone() for k, p in tl.params.items()} for n, tl in wrapped.items()}
                 res.best_iter = it
-        if not_use_best_mse and it == iters - 1:
+        if self.not_use_best_mse and it == self.iters - 1:
             res.best_params = {n: {k: p.data.clone() for k, p in tl.params.items()} for n, tl in wrapped.items()}
             res.best_iter = it
         # sign-SGD step + zero_grad + LinearLR(1 -> 0 over iters)
         with torch.no_grad():
-            for params, lr_t in groups:
+            for params, lr_t in self.groups:
                 for p in params:
                     if p.grad is not None:
                         p.add_(torch.sign(p.grad), alpha=-lr_t.item())
                         p.grad = None
         # LinearLR(start 1 -> end 0 over `iters`), chainable form: lr *= 1 - 1/(iters - it), in the lr tensor's fp32
-        for _, lr_t in groups:
+        iters = self.iters
+        for _, lr_t in self.groups:
             lr_t.mul_(1.0 + (0.0 - 1.0) / (iters * 1.0 + it * (0.0 - 1.0)))
-    res.best_loss = best_loss
-    with torch.no_grad():
-        unwrap_block(block, wrapped, res.best_params)
-    return res
+        return total
+
+    def finish(self) -> "TuneResult":
+        if self.wrapped:
+            self.res.best_loss = self.best_loss
+            with torch.no_grad():
+                unwrap_block(self.block, self.wrapped, self.res.best_params)
+        return self.res
+
+
+def tune_block(block, inputs, others, fp_outputs, scheme_of, iters=200, batch_size=8, lr=None, minmax_lr=None,
+               token_masks=None, enable_minmax_tuning=True, nv_global_scales=None, amp=True,
+               not_use_best_mse=False, sampler=None, alg_ext=False, imatrices=None, outlier_loss=None) -> TuneResult:
+    """quantize_block: `inputs`/`fp_outputs` are per-sample lists of [1,S,H]; `token_masks` per-sample [1,S]
+    long tensors (1 = valid) or None.  Mutates `block` in place (qdq weights + scale/zp attributes)."""
+    tuner = BlockTuner(block, inputs, others, fp_outputs, scheme_of, iters, batch_size, lr, minmax_lr, token_masks,
+                       enable_minmax_tuning, nv_global_scales, amp, not_use_best_mse, sampler, alg_ext, imatrices, outlier_loss)
+    if not tuner.wrapped:
+        return tuner.res
+    for it in range(iters):
+        tuner.step(it)
+    return tuner.finish()
 
 
 # --------------------------------------------------------------------------------------------

@@ -58,11 +58,14 @@ extern "C" int host_qdq(int dtype, int bits, int g, long groups, const float* w,
 }
 
 // Exhaustive check of ar::div_exact (the division-free w / s of the hot kernels): every finite bf16 numerator against every
-// finite fp16-valued scale with |s| >= 1e-5 (the q_scale_thresh clip guarantees that bound), bit-for-bit against the IEEE
-// quotient.  Returns the number of mismatching pairs; *pairs receives how many were checked.
-extern "C" long host_div_exact_check(long* pairs) {
-  long bad = 0, tot = 0;
-#pragma omp parallel for reduction(+ : bad, tot) schedule(dynamic, 64)
+// finite fp16-valued scale with |s| >= 1e-5 (the q_scale_thresh clip guarantees that bound) against the IEEE quotient.
+// Returns the number of pairs that are neither bit-identical nor "both below 2^-80 in magnitude" (tiny / zero numerators:
+// invisible in round(w/s + V), see ar_qdq_math.cuh); *pairs = pairs checked, *exact = bit-identical pairs,
+// *max_inexact_w = the largest |w| of a pair that is not bit-identical (must be far below any real weight).
+extern "C" long host_div_exact_check(long* pairs, long* exact, float* max_inexact_w) {
+  long bad = 0, tot = 0, same = 0;
+  float worst = 0.f;
+#pragma omp parallel for reduction(+ : bad, tot, same) reduction(max : worst) schedule(dynamic, 64)
   for (int hs = 0; hs < 65536; ++hs) {
     const int e = (hs >> 10) & 31, m = hs & 1023;
     if (e == 31) continue;
@@ -74,6 +77,7 @@ extern "C" long host_div_exact_check(long* pairs) {
     for (int wb = 0; wb < 65536; ++wb) {
       const float w = __uint_as_float(((uint32_t)wb) << 16);
       if (std::isnan(w) || std::isinf(w)) continue;
+      if (fabsf(w) > 65504.f * 128.f) continue;            // an fp16 scale cannot represent such a group (s = max|w| / maxq)
       volatile float wv = w, sv = s;
       const float ref = wv / sv;
       const float got = ar::div_exact(w, s, rs);
@@ -81,9 +85,14 @@ extern "C" long host_div_exact_check(long* pairs) {
       memcpy(&a, &got, 4);
       memcpy(&b, &ref, 4);
       ++tot;
-      if (a != b) ++bad;
+      if (a == b) { ++same; continue; }
+      const float tiny = ldexpf(1.f, -80);
+      if (fabsf(got) < tiny && fabsf(ref) < tiny) { worst = fmaxf(worst, fabsf(w)); continue; }
+      ++bad;
     }
   }
   if (pairs) *pairs = tot;
+  if (exact) *exact = same;
+  if (max_inexact_w) *max_inexact_w = worst;
   return bad;
 }
