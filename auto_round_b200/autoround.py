@@ -212,6 +212,8 @@ class AutoRound:
         self._orig_disable_opt_rtn = kwargs.get("disable_opt_rtn")
         self.disable_opt_rtn = bool(kwargs.get("disable_opt_rtn", False))
         self.device = self._resolve_device(device_map)
+        if torch.cuda.is_available():
+            torch.cuda.set_device(self.device)       # the C ABI launches on the current device's current stream
         self.amp_dtype = torch.bfloat16
         self.dp = self._resolve_dp()
         set_seed(seed)
@@ -369,7 +371,7 @@ class AutoRound:
     def _forward_all(self, quantizer: SignRoundQuantizer, block, inputs, others, token_masks):
         """BlockForwardRunner.forward over every sample in batches of `batch_size` (algorithms/block_runner.py:171)."""
         dev = self.device
-        static_kw, per_sample_kw = quantizer._prepare_others(others, token_masks, dev)
+        static_kw, per_sample_kw = quantizer._prepare_others(others, token_masks, dev, block)
         outs = []
         bs = self.batch_size
         n = len(inputs)
@@ -473,6 +475,12 @@ class AutoRound:
             for bj in range(start):
                 snap = resume.load_block(f"{prefix}.{bj}")
                 rng = snap.pop("__rng__", rng)
+                quantizer.block_prefix = f"{prefix}.{bj}"
+                unfuse_experts(blocks[bj])                                # snapshots hold per-expert names
+                for p in blocks[bj].parameters():                         # same normalisation as the live path
+                    p.requires_grad_(False)
+                    if p.dtype in (torch.float32, torch.float16):
+                        p.data = p.data.to(self.amp_dtype)
                 resume_mod.restore_block(blocks[bj], snap, quantizer.scheme_for)
                 self.block_results.append({"block": f"{prefix}.{bj}", "resumed": True})
             fp_inputs = [t.to(self.device) for t in fp_chain]
@@ -484,6 +492,7 @@ class AutoRound:
             if bi < start:
                 continue
             tb = time.time()
+            quantizer.block_prefix = f"{prefix}.{bi}"                     # layer_config keys are full module names
             self._hook(bi, "h2d0")
             block.to(self.device)                                         # H2D of this block's weights
             unfuse_experts(block)                                         # MoE: fused 3-D experts -> per-expert nn.Linear
@@ -554,9 +563,10 @@ class AutoRound:
         self.block_prefix = prefix
         layer_cfg = {}
         for bi, block in enumerate(blocks):
+            quantizer.block_prefix = f"{prefix}.{bi}"
             for n, m in block.named_modules():
                 if hasattr(m, "scale") or isinstance(m, export.QuantLinear):
-                    layer_cfg[f"{prefix}.{bi}.{n}"] = self.scheme.to_dict()
+                    layer_cfg[f"{prefix}.{bi}.{n}"] = quantizer.scheme_for(n, m).to_dict()
         self.layer_config_out = layer_cfg
         return model, layer_cfg
 
@@ -580,6 +590,7 @@ class AutoRound:
     def _quantize_lm_head(self, quantizer, fp_chain, q_chain, ids_cache):
         """orchestrator.py:840-930 -> quantize_layer_outside_block: tune lm_head on (norm(q chain), norm(FP chain))."""
         norm, head, name = self._find_tail()
+        quantizer.block_prefix = None                 # `name` is already a full module name
         norm.to(self.device)
         head.to(self.device)
         for p in list(norm.parameters()) + list(head.parameters()):
@@ -643,6 +654,7 @@ class AutoRound:
         self.quantizer = quantizer
         t0 = time.time()
         for bi, block in enumerate(blocks):
+            quantizer.block_prefix = f"{prefix}.{bi}"
             self._hook(bi, "h2d0")
             block.to(self.device)
             unfuse_experts(block)
@@ -683,6 +695,7 @@ class AutoRound:
         self.quantizer = quantizer
         t0 = time.time()
         for bi, block in enumerate(blocks):
+            quantizer.block_prefix = f"{prefix}.{bi}"
             self._hook(bi, "h2d0")
             block.to(self.device)
             unfuse_experts(block)
@@ -724,19 +737,52 @@ class AutoRound:
             raise RuntimeError("call quantize() first")
         prefix, blocks = self.block_prefix, self._blocks
         if not self._packed:
-            for block in blocks:
+            for bi, block in enumerate(blocks):
+                self.quantizer.block_prefix = f"{prefix}.{bi}"
                 for n, m in list(block.named_modules()):
                     if type(m) is nn.Linear and hasattr(m, "scale"):
                         export.pack_layer(n, block, self.quantizer.scheme_for(n, m), self.device)
+            self.quantizer.block_prefix = None
+            for n in (getattr(self, "_lm_head_extra", None) or {}):        # layers tuned outside the blocks (lm_head)
+                m = self.model.get_submodule(n)
+                if type(m) is nn.Linear and hasattr(m, "scale"):
+                    export.pack_layer(n, self.model, self.quantizer.scheme_for(n, m), self.device)
             self._packed = True
-        qcfg = export.build_quantization_config(self.scheme, prefix, getattr(self, "_lm_head_extra", None), self.iters,
-                                                self.nsamples, self.seqlen, self.batch_size, tuning=self.sign_kw)
+        extra = dict(getattr(self, "_lm_head_extra", None) or {})
+        extra.update(self._layer_config_overrides(prefix, blocks))
+        tuning = dict(self.sign_kw)
+        lr_used = self.quantizer.compute_lr(self.scheme.bits) if self.iters > 0 else None
+        if lr_used is not None and "lr" not in tuning and lr_used != 1.0 / self.iters:
+            tuning["lr"] = lr_used                    # the auto rule gave 2/iters: the reference serialises the resolved lr
+            tuning.setdefault("minmax_lr", lr_used)
+        qcfg = export.build_quantization_config(self.scheme, prefix, extra or None, self.iters,
+                                                self.nsamples, self.seqlen, self.batch_size, tuning=tuning)
         self.quantization_config = qcfg
         if output_dir is None:
             self.model.config.quantization_config = qcfg
             return self.model
         export.save_quantized(self.model, output_dir, qcfg, self.tokenizer)
         return self.model
+
+    def _layer_config_overrides(self, prefix, blocks) -> dict:
+        """`extra_config` entries for block layers whose resolved scheme differs from the global one
+        (export_to_autoround/export.py:303-318): full layer name -> the differing fields."""
+        out = {}
+        if not self.layer_config:
+            return out
+        base = self.scheme.to_dict()
+        for bi, block in enumerate(blocks):
+            self.quantizer.block_prefix = f"{prefix}.{bi}"
+            for n, m in block.named_modules():
+                if type(m) is nn.Linear or isinstance(m, export.QuantLinear):
+                    sc = self.quantizer.scheme_for(n, m)
+                    if sc is None:
+                        continue
+                    diff = {k: v for k, v in sc.to_dict().items() if base.get(k) != v}
+                    if diff:
+                        out[f"{prefix}.{bi}.{n}"] = diff
+        self.quantizer.block_prefix = None
+        return out
 
     def quantize_and_save(self, output_dir: str = "tmp_autoround", format: Optional[str] = None, inplace: bool = True):
         fmt = format or "auto_round"

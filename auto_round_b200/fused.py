@@ -118,6 +118,12 @@ def _fused_mlp_forward(self, x):
     return self.down_proj(self.act_fn(g) * u)
 
 
+# RMSNorm classes whose forward is exactly `w * (x * rsqrt(mean(x^2) + eps)).to(dtype)` (verified against the HF sources):
+# an allowlist, because (1 + w) variants (Gemma, Qwen3-Next) share the class-name suffix but not the formula
+_PLAIN_RMSNORM = {"LlamaRMSNorm", "Qwen2RMSNorm", "Qwen3RMSNorm", "MistralRMSNorm", "MixtralRMSNorm", "Qwen2MoeRMSNorm",
+                  "Qwen3MoeRMSNorm", "Phi3RMSNorm"}
+
+
 class fused_block_ops:
     """Context manager: patch RMSNorm modules, SwiGLU MLPs and the rotary helper of `block`; restore on exit."""
 
@@ -131,9 +137,9 @@ class fused_block_ops:
         from .wrapper import set_module
         for name, m in list(self.block.named_modules()):
             cls = type(m).__name__
-            if cls.endswith("RMSNorm") and hasattr(m, "weight") and m.weight is not None and m.weight.dim() == 1 \
+            if cls in _PLAIN_RMSNORM and hasattr(m, "weight") and m.weight is not None and m.weight.dim() == 1 \
                     and m.weight.is_cuda and m.weight.shape[0] % 8 == 0 and m.weight.shape[0] <= 8192 \
-                    and (hasattr(m, "variance_epsilon") or hasattr(m, "eps")) and "Gemma" not in cls:
+                    and (hasattr(m, "variance_epsilon") or hasattr(m, "eps")):
                 self.norms.append((name, m))
                 set_module(self.block, name, FusedRMSNorm(m))
             elif all(hasattr(m, a) for a in ("gate_proj", "up_proj", "down_proj", "act_fn")) and _is_silu(m.act_fn) \

@@ -218,6 +218,20 @@ def _causal_equivalent(masks, token_masks) -> bool:
     return True
 
 
+def _causal_when_unmasked(block: Optional[nn.Module]) -> bool:
+    """True if every attention module of `block` runs causal attention when it gets attention_mask=None (HF sdpa and
+    flash-attention integrations derive is_causal from the module); False for `eager` (or unknown) implementations."""
+    if block is None:
+        return False
+    impls = set()
+    for m in block.modules():
+        cfg = getattr(m, "config", None)
+        impl = getattr(cfg, "_attn_implementation", None) if cfg is not None else None
+        if impl is not None:
+            impls.add(impl)
+    return bool(impls) and impls <= {"sdpa", "flash_attention_2", "flash_attention_3"}
+
+
 class SignRoundQuantizer:
     """Tuning loop driver.  Hyper-parameters follow SignRoundConfig (sign_round/config.py:21-178)."""
 
@@ -260,10 +274,15 @@ class SignRoundQuantizer:
         return 1.0 / max(self.iters, 1)
 
     def scheme_for(self, name: str, module: nn.Module) -> Optional[QuantizationScheme]:
-        cfg = self.layer_config.get(name)
+        """Per-layer override: `layer_config` keys are FULL module names as in the reference
+        ("model.layers.3.mlp.down_proj": {"bits": 8}); `self.block_prefix` ("model.layers.3", set by AutoRound before each
+        block) turns the block-relative `name` into one.  A bare block-relative key applies to that layer of every block."""
+        cfg = None
+        prefix = getattr(self, "block_prefix", None)
+        if prefix:
+            cfg = self.layer_config.get(f"{prefix}.{name}")
         if cfg is None:
-            g = getattr(module, "global_name", None)
-            cfg = self.layer_config.get(g) if g else None
+            cfg = self.layer_config.get(name)
         if cfg is None:
             return self.scheme
         if isinstance(cfg, QuantizationScheme):
@@ -343,14 +362,16 @@ class SignRoundQuantizer:
         t = torch.cat([s.to(device, non_blocking=True) for s in samples], dim=0)
         return t.contiguous()
 
-    def _prepare_others(self, input_others: dict, token_masks, device):
-        """Split block kwargs into (static kwargs, per-sample stacked tensors); drop a causal-equivalent mask."""
+    def _prepare_others(self, input_others: dict, token_masks, device, block: Optional[nn.Module] = None):
+        """Split block kwargs into (static kwargs, per-sample stacked tensors); drop a causal-equivalent mask -- but only
+        when the block's attention takes the `is_causal` path for a missing mask (sdpa / flash); HF's eager attention applies
+        NO mask at all when attention_mask is None, so there the cached mask is kept."""
         static, per_sample = {}, {}
         others = dict(input_others or {})
         others.pop("positional_inputs", None)
         am = others.get("attention_mask")
         if isinstance(am, (list, tuple)) and len(am) and isinstance(am[0], torch.Tensor):
-            if _causal_equivalent(am, token_masks):
+            if _causal_when_unmasked(block) and _causal_equivalent(am, token_masks):
                 others["attention_mask"] = None          # -> is_causal fast path inside the HF attention
         for key, val in others.items():
             if key in SHARED_CACHE_KEYS:
@@ -375,6 +396,13 @@ class SignRoundQuantizer:
     # ---------------------------------------------------------------------------------------------
     def quantize_block(self, block: nn.Module, fp_inputs, input_others, fp_outputs, q_inputs=None, block_ctx=None,
                        input_ids=None, nv_global_scales: Optional[dict] = None, **kwargs) -> dict:
+        # the C ABI launches on the CURRENT device's current stream: make the block's device current for the whole call
+        with torch.cuda.device(next(block.parameters()).device):
+            return self._quantize_block(block, fp_inputs, input_others, fp_outputs, q_inputs, block_ctx, input_ids,
+                                        nv_global_scales, **kwargs)
+
+    def _quantize_block(self, block: nn.Module, fp_inputs, input_others, fp_outputs, q_inputs=None, block_ctx=None,
+                        input_ids=None, nv_global_scales: Optional[dict] = None, **kwargs) -> dict:
         dp = self.dp
         active = q_inputs if (q_inputs is not None and self.enable_quanted_input) else fp_inputs
         device = next(block.parameters()).device
@@ -402,7 +430,7 @@ class SignRoundQuantizer:
             return {}
 
         static_kw, per_sample_kw = self._prepare_others(
-            input_others, None if token_masks is None else list(token_masks), device)
+            input_others, None if token_masks is None else list(token_masks), device, block)
 
         # ---- schedules drawn up-front (same python-random stream as the reference's IndexSampler)
         iters = self.iters
@@ -625,6 +653,7 @@ class SignRoundQuantizer:
         device = layer.weight.device
         if not layer.weight.is_cuda:
             raise RuntimeError("quantize_layer: the layer must be on a CUDA device (no CPU tuning path)")
+        torch.cuda.set_device(device)                              # the C ABI launches on the current device's stream
         if self.dp.world > 1:
             raise NotImplementedError("quantize_layer under data parallelism (every rank would repeat the same work)")
         sc = self.scheme_for(name, layer)

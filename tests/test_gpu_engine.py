@@ -213,3 +213,37 @@ def test_autoround_model_level(golden_dir, tag, tmp_path):
     cfg = json.load(open(os.path.join(out_dir, "config.json")))["quantization_config"]
     assert cfg["quant_method"] == "auto-round" and cfg["bits"] == 4
     assert cfg["packing_format"] == ("auto_round:auto_gptq" if tag.startswith("w4") else "auto_round:llm_compressor")
+
+
+def test_eager_attention_block_keeps_cached_mask(golden_dir):
+    """with attn_implementation='eager' HF applies NO mask when attention_mask is None, so the engine must keep
+    the cached mask there.  A bool causal mask (what transformers >= 5 caches) on an eager block must give the loss the
+    oracle gets with the same mask through sdpa -- bidirectional attention would be off by orders of magnitude."""
+    from transformers.models.llama.modeling_llama import LlamaDecoderLayer
+
+    rec = _load(golden_dir, "w4a16_sym_g32")
+    b = rec["blocks"][0]
+    osc = S.LayerScheme(4, 32, True, "int")
+    masks = [(ids != -100).to(torch.long) for ids in b["input_ids"]]
+    seq = b["inputs"][0].shape[1]
+    causal = torch.ones(seq, seq, dtype=torch.bool).tril().reshape(1, 1, seq, seq)
+    others = dict(b["others"])
+    others["attention_mask"] = [causal.clone() for _ in b["inputs"]]
+    iters = 6
+    oblk = _tiny_block(b["block_state"])
+    with torch.no_grad():
+        refs = [S.block_forward(oblk, *S.select_batch(b["inputs"], others, [i])) for i in range(len(b["inputs"]))]
+    batches = [[0, 1, 2, 3]] * iters
+    ores = S.tune_block(oblk, b["inputs"], others, refs, lambda n, m: osc, iters=iters, batch_size=4, token_masks=masks,
+                        sampler=S.ReplaySampler(batches))
+    cfg = _tiny_cfg()
+    cfg._attn_implementation = "eager"
+    blk = LlamaDecoderLayer(cfg, 0).to(torch.bfloat16).eval()
+    blk.load_state_dict(b["block_state"])
+    blk = blk.to(DEV)
+    for p in blk.parameters():
+        p.requires_grad_(False)
+    q = SignRoundQuantizer(parse_scheme("W4A16", {"group_size": 32}), iters=iters, batch_size=4)
+    q.quantize_block(blk, [t.to(DEV) for t in b["inputs"]], others, [t.to(DEV) for t in refs], None, None,
+                     input_ids=b["input_ids"], sampler=S.ReplaySampler(batches))
+    assert q.last_result.losses[0] == pytest.approx(ores.losses[0], rel=3e-2)

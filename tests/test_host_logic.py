@@ -66,3 +66,60 @@ def test_importance_weights_zero_repair_matches_oracle(golden_dir):
     got3 = importance_weights(im3, r2["w"], 4, 128)
     g3, _, _ = Q.to_groups(r2["w"], 128)
     assert torch.equal(got3.reshape(-1, 128), Q.imatrix_weights(im3, g3, 4, 128))
+
+
+def test_layer_config_keys_are_full_module_names():
+    """reference-style keys ("model.layers.3.mlp.down_proj": {...}) must reach the layer of THAT block only."""
+    import torch.nn as nn
+
+    from auto_round_b200.quantizer import SignRoundQuantizer
+    from auto_round_b200.schemes import parse_scheme
+
+    q = SignRoundQuantizer(parse_scheme("W4A16"), iters=1,
+                           layer_config={"model.layers.3.mlp.down_proj": {"bits": 8}, "self_attn.o_proj": {"group_size": 32},
+                                         "model.layers.1.mlp.up_proj": {"bits": 16}})
+    lin = nn.Linear(8, 8)
+    q.block_prefix = "model.layers.3"
+    assert q.scheme_for("mlp.down_proj", lin).bits == 8
+    assert q.scheme_for("mlp.up_proj", lin).bits == 4
+    assert q.scheme_for("self_attn.o_proj", lin).group_size == 32       # bare block-relative key: every block
+    q.block_prefix = "model.layers.1"
+    assert q.scheme_for("mlp.down_proj", lin).bits == 4
+    assert q.scheme_for("mlp.up_proj", lin).bits == 16                  # > 8 bits: wrapper_block leaves the layer alone
+    assert q.scheme_for("self_attn.o_proj", lin).group_size == 32
+
+
+def test_causal_mask_is_only_dropped_for_sdpa_or_flash_attention():
+    """HF's eager attention applies NO mask when attention_mask is None, so the cached causal mask may only be
+    dropped (-> is_causal fast path) for the sdpa / flash integrations."""
+    import torch
+    import torch.nn as nn
+
+    from auto_round_b200.quantizer import SignRoundQuantizer, _causal_when_unmasked
+    from auto_round_b200.schemes import parse_scheme
+
+    class Cfg:
+        def __init__(self, impl):
+            self._attn_implementation = impl
+
+    class Attn(nn.Module):
+        def __init__(self, impl):
+            super().__init__()
+            self.config = Cfg(impl)
+
+    class Block(nn.Module):
+        def __init__(self, impl):
+            super().__init__()
+            self.self_attn = Attn(impl)
+
+    assert _causal_when_unmasked(Block("sdpa")) and _causal_when_unmasked(Block("flash_attention_2"))
+    assert not _causal_when_unmasked(Block("eager")) and not _causal_when_unmasked(nn.Linear(2, 2)) and not _causal_when_unmasked(None)
+    s = 6
+    causal = torch.ones(s, s, dtype=torch.bool).tril().reshape(1, 1, s, s)
+    masks = [causal.clone(), causal.clone()]
+    tok = [torch.ones(s, dtype=torch.uint8), torch.ones(s, dtype=torch.uint8)]
+    q = SignRoundQuantizer(parse_scheme("W4A16"), iters=1)
+    st, per = q._prepare_others({"attention_mask": masks}, tok, "cpu", Block("sdpa"))
+    assert st.get("attention_mask", "absent") is None and "attention_mask" not in per
+    st, per = q._prepare_others({"attention_mask": masks}, tok, "cpu", Block("eager"))
+    assert "attention_mask" in per and per["attention_mask"].shape == (2, 1, s, s)
