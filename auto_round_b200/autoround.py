@@ -138,7 +138,11 @@ class _swap_linears:
         self.saved = []
 
     def __enter__(self):
+        from .moe import GroupedExperts
+        grouped = tuple(n + "." for n, m in self.block.named_modules() if isinstance(m, GroupedExperts))
         for name, m in list(self.block.named_modules()):
+            if name.startswith(grouped) and grouped:
+                continue                     # expert linears are never called: the grouped GEMMs read their stacked weights
             if type(m) is nn.Linear and m.weight.is_cuda and m.weight.dtype == torch.bfloat16 \
                     and m.weight.shape[1] % 8 == 0 and m.weight.shape[0] % 8 == 0:
                 self.saved.append((name, m))

@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libar_b200.so")
-SOURCES = ["ar_capi.cu", "ar_qdq.cu", "ar_pack.cu", "ar_loop.cu", "ar_block.cu", "ar_search.cu", "ar_outlier.cu", "ar_gemm.cu"]
+SOURCES = ["ar_capi.cu", "ar_qdq.cu", "ar_pack.cu", "ar_loop.cu", "ar_block.cu", "ar_search.cu", "ar_outlier.cu", "ar_moe.cu", "ar_gemm.cu"]
 HEADERS = ["ar_common.cuh", "ar_qdq_math.cuh", os.path.join("..", "..", "include", "ar_b200.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]

@@ -271,8 +271,34 @@ struct DwParams {                 // EPI_DW: fake-quant backward inputs/outputs
   const float* init;              // ar_qspec::init_scale (alg_ext) or null
 };
 
+// Grouped (ragged per-expert) GEMMs of the MoE path: tiles are resolved through small device-side tables written by the
+// routing kernel of the same iteration (ar_moe_route), so launches stay static and graph-capturable.
+//   GROUP_M  forward / grad-in of all experts in one launch: A rows are the routed tokens sorted by expert, every expert's
+//            segment padded to the 256-row tile; table[i] = {m0, expert}; B (the stacked per-expert weights) is offset by
+//            expert * b_group_rows (a row offset for a K-major B, a reduction offset for an MN-major B)
+//   GROUP_K  grad-w: one [N, K] output per ACTIVE expert, reduction over that expert's token rows;
+//            table[i] = {expert, k_off, k_len}; D rows are offset by expert * d_group_rows
+enum { GROUP_NONE = 0, GROUP_M = 1, GROUP_K = 2 };
+struct GroupDesc {
+  int mode;
+  const int32_t* table;
+  const int32_t* num;             // device scalar: entries in `table`
+  int b_group_rows;
+  int d_group_rows;
+};
+
+struct TileInfo {
+  int m0, n0;                     // A-row / B-row coordinate of the tile (before the CTA-pair split)
+  int d_m0, d_n0;                 // output coordinates
+  int a_koff, b_koff;             // reduction-coordinate offsets of the A / B loads
+  int num_kb;
+};
+
 struct GemmParams {
   int m, n, k;                    // logical problem: D[m,n] = A[m,k] B[n,k]^T
+  GroupDesc grp;
+  // host-only (grouped launches): extents of the tensor maps when they differ from the logical problem, and the tile bound
+  int b_rows_map, b_k_map, d_rows_map, max_tiles;
   int m_tiles, n_tiles;
   const uint16_t* bias;           // EPI_STORE, optional [n]
   unsigned int* tile_ctr;         // dynamic tile scheduler: ticket counter of this launch (0 at launch, reset to 0 at exit)
@@ -307,6 +333,41 @@ __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int
   const int in = t - grp * per_group;
   mt = first + in % gm;
   nt = in / gm;
+}
+
+template <int BN, int CG, bool B_MN>
+__device__ __forceinline__ TileInfo resolve_tile(const GemmParams& p, int t, int m_tiles, int num_kb_static) {
+  TileInfo ti;
+  int mt, nt;
+  if (p.grp.mode == GROUP_K) {
+    const int per = p.m_tiles * p.n_tiles;
+    const int ae = t / per;
+    tile_coords(t - ae * per, p.m_tiles, p.n_tiles, mt, nt);
+    const int e = p.grp.table[3 * ae], koff = p.grp.table[3 * ae + 1], klen = p.grp.table[3 * ae + 2];
+    ti.m0 = mt * (BLOCK_M * CG);
+    ti.n0 = nt * BN;
+    ti.d_m0 = e * p.grp.d_group_rows + ti.m0;
+    ti.d_n0 = ti.n0;
+    ti.a_koff = koff;
+    ti.b_koff = koff;
+    ti.num_kb = klen / BLOCK_K;
+    return ti;
+  }
+  tile_coords(t, m_tiles, p.n_tiles, mt, nt);
+  ti.n0 = nt * BN;
+  ti.d_n0 = ti.n0;
+  ti.a_koff = 0;
+  ti.b_koff = 0;
+  ti.num_kb = num_kb_static;
+  if (p.grp.mode == GROUP_M) {
+    const int m0 = p.grp.table[2 * mt], e = p.grp.table[2 * mt + 1];
+    ti.m0 = m0;
+    if (B_MN) ti.b_koff = e * p.grp.b_group_rows; else ti.n0 += e * p.grp.b_group_rows;
+  } else {
+    ti.m0 = mt * (BLOCK_M * CG);
+  }
+  ti.d_m0 = ti.m0;
+  return ti;
 }
 
 // ------------------------------------------------------------------------------------- dW fused epilogue
@@ -464,7 +525,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;     // rank inside the CTA pair
   const bool leader = (cta_rank == 0);
   const int num_units = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;   // scheduling unit: CTA or CTA pair
-  const int num_tiles = p.m_tiles * p.n_tiles;     // m_tiles counts (128*CG)-row tiles
+  // m_tiles counts (128*CG)-row tiles; grouped launches read their tile count from the routing kernel's output
+  const int grp_num = (p.grp.mode != GROUP_NONE) ? *p.grp.num : 0;
+  const int m_tiles_dyn = (p.grp.mode == GROUP_M) ? grp_num : p.m_tiles;
+  const int num_tiles = (p.grp.mode == GROUP_K) ? grp_num * p.m_tiles * p.n_tiles : m_tiles_dyn * p.n_tiles;
   const int num_kb = (p.k + BLOCK_K - 1) / BLOCK_K;
   constexpr uint32_t kTmemCols = 2 * BN;       // two accumulator stages (256 or 512: powers of two)
   // consumers of a ticket: leader MMA warp + 4 epilogue warps (+ the peer's producer and its 4 epilogue warps)
@@ -524,11 +588,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           t = take_ticket(n, true, false);
           if (t >= num_tiles) break;
         }
-        int mt, nt;
-        tile_coords(t, p.m_tiles, p.n_tiles, mt, nt);
-        const int m0 = mt * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M;        // this CTA's 128 rows of A / D
-        const int n0 = nt * BN + (int)cta_rank * L::kBRows;                  // this CTA's share of the B rows
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const TileInfo ti = resolve_tile<BN, CG, B_MN>(p, t, m_tiles_dyn, num_kb);
+        const int m0 = ti.m0 + (int)cta_rank * BLOCK_M;                      // this CTA's 128 rows of A / D
+        const int n0 = ti.n0 + (int)cta_rank * L::kBRows;                    // this CTA's share of the B rows
+        for (int kb = 0; kb < ti.num_kb; ++kb, ++it) {
           const uint32_t s = it % kNS, ph = (it / kNS) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
           if (CG == 1) mbar_expect_tx(&full[s], L::kABytes + L::kBBytes);
@@ -541,18 +604,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             if (CG == 2) tma_load_2d_2sm(dst, map, &full[s], c0, c1); else tma_load_2d(dst, map, &full[s], c0, c1);
           };
           if (!A_MN) {
-            load(sa, &map_a, k0, m0);                                        // box {64 k, 128 m}
+            load(sa, &map_a, ti.a_koff + k0, m0);                            // box {64 k, 128 m}
           } else {
 #pragma unroll
             for (int i = 0; i < BLOCK_M / 64; ++i)                           // box {64 m, 64 k} per 64-wide atom
-              load(sa + i * (64 * BLOCK_K * 2), &map_a, m0 + i * 64, k0);
+              load(sa + i * (64 * BLOCK_K * 2), &map_a, m0 + i * 64, ti.a_koff + k0);
           }
           if (!B_MN) {
-            load(sb, &map_b, k0, n0);                                        // box {64 k, kBRows n}
+            load(sb, &map_b, ti.b_koff + k0, n0);                            // box {64 k, kBRows n}
           } else {
 #pragma unroll
             for (int i = 0; i < L::kBRows / 64; ++i)
-              load(sb + i * (64 * BLOCK_K * 2), &map_b, n0 + i * 64, k0);
+              load(sb + i * (64 * BLOCK_K * 2), &map_b, n0 + i * 64, ti.b_koff + k0);
           }
         }
         if (leader) t = t_next;
@@ -571,11 +634,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     for (uint32_t local_tile = 0;; ++local_tile) {
       const int t = take_ticket(local_tile, lane == 0, true);
       if (t >= num_tiles) break;
+      const int tile_kb = (p.grp.mode == GROUP_K) ? p.grp.table[3 * (t / (p.m_tiles * p.n_tiles)) + 2] / BLOCK_K : num_kb;
       const uint32_t as = local_tile & 1u, aph = (local_tile >> 1) & 1u;
       mbar_wait(&tempty[as], aph ^ 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+      for (int kb = 0; kb < tile_kb; ++kb, ++it) {
         const uint32_t s = it % kNS, ph = (it / kNS) & 1u;
         mbar_wait(&full[s], ph);
         tc_fence_after();
@@ -591,10 +655,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           }
           if (CG == 2) {
             umma_commit_2sm(&empty[s]);                        // frees the stage in BOTH CTAs when these MMAs retire
-            if (kb == num_kb - 1) umma_commit_2sm(&tfull[as]); // accumulator complete -> both epilogues
+            if (kb == tile_kb - 1) umma_commit_2sm(&tfull[as]); // accumulator complete -> both epilogues
           } else {
             umma_commit(&empty[s]);
-            if (kb == num_kb - 1) umma_commit(&tfull[as]);
+            if (kb == tile_kb - 1) umma_commit(&tfull[as]);
           }
         }
         __syncwarp();
@@ -609,9 +673,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     for (uint32_t local_tile = 0;; ++local_tile) {
       const int t = take_ticket(local_tile, lane == 0, true);
       if (t >= num_tiles) break;
-      int mt, nt;
-      tile_coords(t, p.m_tiles, p.n_tiles, mt, nt);
-      const int m0 = mt * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M, n0 = nt * BN;
+      const TileInfo ti = resolve_tile<BN, CG, B_MN>(p, t, m_tiles_dyn, num_kb);
+      const int m0 = ti.d_m0 + (int)cta_rank * BLOCK_M, n0 = ti.d_n0;
       const uint32_t as = local_tile & 1u, aph = (local_tile >> 1) & 1u;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
@@ -764,11 +827,14 @@ static int launch_cg(const void* a, const void* b, void* d, int m, int n, int k,
   if (!A_MN) rc = make_map(&ma, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, 64, BLOCK_M);   // stored [m, k]
   else rc = make_map(&ma, a, (uint64_t)m, (uint64_t)k, (uint64_t)lda, 64, BLOCK_K);          // stored [k, m]
   if (rc) return rc;
-  if (!B_MN) rc = make_map(&mb, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, 64, L::kBRows);
-  else rc = make_map(&mb, b, (uint64_t)n, (uint64_t)k, (uint64_t)ldb, 64, BLOCK_K);
+  const uint64_t b_rows = base.b_rows_map > 0 ? (uint64_t)base.b_rows_map : (uint64_t)n;
+  const uint64_t b_k = base.b_k_map > 0 ? (uint64_t)base.b_k_map : (uint64_t)k;
+  const uint64_t d_rows = base.d_rows_map > 0 ? (uint64_t)base.d_rows_map : (uint64_t)m;
+  if (!B_MN) rc = make_map(&mb, b, b_k, b_rows, (uint64_t)ldb, 64, L::kBRows);
+  else rc = make_map(&mb, b, b_rows, b_k, (uint64_t)ldb, 64, BLOCK_K);
   if (rc) return rc;
   if (EPI == EPI_STORE) {
-    rc = make_map(&md, d, (uint64_t)n, (uint64_t)m, (uint64_t)ldd, 64, BLOCK_M);
+    rc = make_map(&md, d, (uint64_t)n, d_rows, (uint64_t)ldd, 64, BLOCK_M);
     if (rc) return rc;
   } else {
     md = ma;
@@ -779,7 +845,7 @@ static int launch_cg(const void* a, const void* b, void* d, int m, int n, int k,
   AR_REQUIRE(p.tile_ctr != nullptr, AR_E_DRIVER, "tile counter symbol not available on this device");
   p.m_tiles = (m + BLOCK_M * CG - 1) / (BLOCK_M * CG);
   p.n_tiles = (n + BN - 1) / BN;
-  const int tiles = p.m_tiles * p.n_tiles;
+  const int tiles = base.max_tiles > 0 ? base.max_tiles : p.m_tiles * p.n_tiles;
   const int max_units = sm_count() / CG;
   const int units = tiles < max_units ? tiles : max_units;
   cudaLaunchConfig_t cfg{};
@@ -837,6 +903,43 @@ extern "C" int ar_gemm_bf16(const void* a, const void* b, void* d, int m, int n,
   if (!a_mn && b_mn) return launch<false, true, 256, EPI_STORE, NoCtx, 32, false>(a, b, d, m, n, k, lda, ldb, ldd, p, st);
   if (a_mn && !b_mn) return launch<true, false, 256, EPI_STORE, NoCtx, 32, false>(a, b, d, m, n, k, lda, ldb, ldd, p, st);
   return launch<true, true, 256, EPI_STORE, NoCtx, 32, false>(a, b, d, m, n, k, lda, ldb, ldd, p, st);
+}
+
+extern "C" int ar_gemm_bf16_grouped(const void* a, const void* b, void* d, int mode, int rows, int n, int k, int a_mn, int b_mn,
+                                    int64_t lda, int64_t ldb, int64_t ldd, int group_rows, int num_groups,
+                                    const int32_t* table, const int32_t* num, int max_entries, void* stream) {
+  AR_REQUIRE(a && b && d && table && num && rows > 0 && n > 0 && k > 0 && group_rows > 0 && num_groups > 0 && max_entries > 0,
+             AR_E_BADARG, "bad grouped gemm args");
+  AR_REQUIRE(mode == GROUP_M || mode == GROUP_K, AR_E_BADARG, "mode must be 1 (GROUP_M) or 2 (GROUP_K)");
+  if (int rc = check_device()) return rc;
+  GemmParams p{};
+  p.grp.mode = mode;
+  p.grp.table = table;
+  p.grp.num = num;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == GROUP_M) {
+    // D[rows, n] = A[rows, k] * B_e^T, e = expert of the row tile.  B stacked over experts: K-major [G * group_rows, k]
+    // (forward: group_rows = n) or stored [G * group_rows, n] read MN-major with the reduction inside the expert's rows
+    // (grad-in: group_rows = k)
+    AR_REQUIRE(!a_mn, AR_E_UNSUPPORTED, "GROUP_M: A must be K-major");
+    AR_REQUIRE(rows % 256 == 0, AR_E_UNSUPPORTED, "GROUP_M: the padded row count must be a multiple of 256");
+    p.grp.b_group_rows = group_rows;
+    p.max_tiles = max_entries * ((n + 255) / 256);
+    if (!b_mn) {
+      p.b_rows_map = group_rows * num_groups;
+      return launch_cg<false, false, 256, EPI_STORE, NoCtx, 32, false, 2>(a, b, d, rows, n, k, lda, ldb, ldd, p, st);
+    }
+    p.b_k_map = group_rows * num_groups;
+    return launch_cg<false, true, 256, EPI_STORE, NoCtx, 32, false, 2>(a, b, d, rows, n, k, lda, ldb, ldd, p, st);
+  }
+  // GROUP_K: D_e[n_out = `n`... ] -- here the logical problem per active expert is D[m = group_rows, n] = A^T B over that
+  // expert's rows; A stored [rows, m] and B stored [rows, n] (both MN-major), D stacked [G * group_rows, n]
+  AR_REQUIRE(a_mn && b_mn, AR_E_UNSUPPORTED, "GROUP_K: A and B must be MN-major (stored [rows, features])");
+  AR_REQUIRE(group_rows % 256 == 0, AR_E_UNSUPPORTED, "GROUP_K: output rows per expert must be a multiple of 256");
+  p.grp.d_group_rows = group_rows;
+  p.d_rows_map = group_rows * num_groups;
+  p.max_tiles = max_entries * (group_rows / 256) * ((n + 255) / 256);
+  return launch_cg<true, true, 256, EPI_STORE, NoCtx, 32, false, 2>(a, b, d, group_rows, n, rows, lda, ldb, ldd, p, st);
 }
 
 extern "C" int ar_fq_linear_fwd(const ar_qspec* q, const void* x, int64_t t, const void* w, const float* v, const float* mn,

@@ -339,6 +339,94 @@ def unpack_fp4(packed, n, k):
     return out
 
 
+# ------------------------------------------------------------------------- MoE: routing + grouped GEMMs (csrc/ar_moe.cu)
+class MoeRoute:
+    """Device-side routing tables of one iteration (ar_moe_route): static shapes, filled in the stream."""
+
+    def __init__(self, pairs: int, e_local: int, device):
+        self.pairs, self.e_local = pairs, e_local
+        self.max_rows = (pairs + 255 * e_local + 255) // 256 * 256
+        i32 = dict(dtype=torch.int32, device=device)
+        self.counts = torch.zeros(e_local, **i32)
+        self.offsets = torch.zeros(e_local + 1, **i32)
+        self.row_of_pair = torch.zeros(pairs, **i32)
+        self.pair_of_row = torch.zeros(self.max_rows, **i32)
+        self.mtab = torch.zeros(2 * (self.max_rows // 256), **i32)
+        self.num_mt = torch.zeros(1, **i32)
+        self.ktab = torch.zeros(3 * e_local, **i32)
+        self.num_active = torch.zeros(1, **i32)
+
+
+def moe_route(route: MoeRoute, expert_ids, e_begin=0):
+    _want(expert_ids, torch.int64, "expert_ids")
+    if expert_ids.numel() != route.pairs:
+        raise ValueError("expert_ids does not match the route's pair count")
+    _check(_lib.load().ar_moe_route(_p(expert_ids), route.pairs, int(e_begin), route.e_local, route.max_rows, _p(route.counts),
+                                    _p(route.offsets), _p(route.row_of_pair), _p(route.pair_of_row), _p(route.mtab),
+                                    _p(route.num_mt), _p(route.ktab), _p(route.num_active), _stream()), "ar_moe_route")
+    return route
+
+
+def moe_gather(x2d, route: MoeRoute, topk, pair_w=None, out=None):
+    _want(x2d, torch.bfloat16, "x")
+    _want(pair_w, torch.bfloat16, "pair_w")
+    cols = x2d.shape[1]
+    if out is None:
+        out = torch.empty(route.max_rows, cols, dtype=torch.bfloat16, device=x2d.device)
+    _check(_lib.load().ar_moe_gather(_p(x2d), _p(route.pair_of_row), _p(pair_w), int(topk), route.max_rows, cols, _p(out),
+                                     _stream()), "ar_moe_gather")
+    return out
+
+
+def moe_combine(d, route: MoeRoute, tokens, topk, pair_w=None, d2=None, out=None):
+    _want(d, torch.bfloat16, "d")
+    _want(d2, torch.bfloat16, "d2")
+    _want(pair_w, torch.bfloat16, "pair_w")
+    cols = d.shape[1]
+    if out is None:
+        out = torch.empty(tokens, cols, dtype=torch.bfloat16, device=d.device)
+    _check(_lib.load().ar_moe_combine(_p(d), _p(d2), _p(route.row_of_pair), _p(pair_w), int(tokens), int(topk), cols, _p(out),
+                                      _stream()), "ar_moe_combine")
+    return out
+
+
+def moe_rowdot(g2d, d, route: MoeRoute, topk):
+    _want(g2d, torch.bfloat16, "g")
+    _want(d, torch.bfloat16, "d")
+    dw = torch.empty(route.pairs, dtype=torch.bfloat16, device=d.device)
+    _check(_lib.load().ar_moe_rowdot(_p(g2d), _p(d), _p(route.row_of_pair), route.pairs, int(topk), d.shape[1], _p(dw), _stream()),
+           "ar_moe_rowdot")
+    return dw
+
+
+def gemm_grouped_m(a, b_stack, route: MoeRoute, n, k, b_mn_major=False, out=None):
+    """GROUP_M: out[rows, n] = a[rows, k] · B_eᵀ per 256-row tile.  b_stack: [E, n, k] (forward) or, with b_mn_major,
+    [E, k, n] read as the MN-major operand (grad-in: reduction over the expert's k rows)."""
+    _want(a, torch.bfloat16, "a")
+    _want(b_stack, torch.bfloat16, "b")
+    rows = route.max_rows
+    e = b_stack.shape[0]
+    if out is None:
+        out = torch.empty(rows, n, dtype=torch.bfloat16, device=a.device)
+    group_rows = k if b_mn_major else n
+    _check(_lib.load().ar_gemm_bf16_grouped(_p(a), _p(b_stack), _p(out), 1, rows, n, k, 0, int(b_mn_major), a.stride(0),
+                                            b_stack.stride(1), out.stride(0), group_rows, e, _p(route.mtab), _p(route.num_mt),
+                                            rows // 256, _stream()), "ar_gemm_bf16_grouped")
+    return out
+
+
+def gemm_grouped_k(dy, x, route: MoeRoute, out_stack):
+    """GROUP_K: out_stack[e] ([E, n_out, k_out]) = dy[rows_e, :n_out]ᵀ · x[rows_e, :k_out] for every expert with tokens."""
+    _want(dy, torch.bfloat16, "dy")
+    _want(x, torch.bfloat16, "x")
+    _want(out_stack, torch.bfloat16, "out")
+    e, n_out, k_out = out_stack.shape
+    _check(_lib.load().ar_gemm_bf16_grouped(_p(dy), _p(x), _p(out_stack), 2, route.max_rows, k_out, route.max_rows, 1, 1,
+                                            dy.stride(0), x.stride(0), out_stack.stride(1), n_out, e, _p(route.ktab),
+                                            _p(route.num_active), route.e_local, _stream()), "ar_gemm_bf16_grouped")
+    return out_stack
+
+
 # ------------------------------------------------------------------- fused block glue (csrc/ar_block.cu)
 def rmsnorm_fwd(x2d, w, eps):
     _want(x2d, torch.bfloat16, "x")

@@ -469,8 +469,15 @@ class SignRoundQuantizer:
         else:
             inv_tab = torch.ones(iters, dtype=torch.float64, device=device)
 
-        from .moe import LinearLoopExperts
-        has_moe = any(isinstance(m, LinearLoopExperts) for m in block.modules())   # ragged, data-dependent shapes
+        from .moe import GroupedExperts
+        moe_mods = [m for m in block.modules() if isinstance(m, GroupedExperts)]
+        for m in moe_mods:          # expert WrapperLinears read / write slices of stacked [E, N, K] buffers; under data
+            m.bind_wrapped(dp)      # parallelism the experts are sharded over the ranks (expert parallelism)
+        ep_owned = {}               # id(expert WrapperLinear) -> this rank owns it (full local update, no exchange)
+        for m in moe_mods:
+            for e in range(m.num_experts):
+                for pj in ("gate_proj", "up_proj", "down_proj"):
+                    ep_owned[id(m.layer(e, pj))] = (m.owner_of(e) == dp.rank) if dp.world > 1 else True
 
         # enable_alg_ext loss (SignRoundV2Quantizer._get_loss, sign_roundv2/quantizer.py:362-399): bits < 4 -> the numel/1000
         # largest |pred - ref| are dropped; otherwise it falls back to the base MSE WITHOUT forwarding the valid-token mask
@@ -494,16 +501,10 @@ class SignRoundQuantizer:
         shards, gq_shard = {}, {}
         for n, wl in wrapped.items():
             wl.refresh_wq()                                         # iteration 0 runs on qdq(W; V = 0, scales = 1)
-            shards[n] = dp.row_shard(wl.spec.n)
+            shards[n] = None if id(wl) in ep_owned else dp.row_shard(wl.spec.n)
             if shards[n] is not None:
                 r0, r1 = shards[n]
                 gq_shard[n] = torch.empty(r1 - r0, wl.spec.k, dtype=torch.bfloat16, device=device)
-        # MoE under data parallelism: which experts receive a gradient differs per rank, so the collectives cannot be issued
-        # from the backward hooks (their order would differ); they run after the backward in layer order, and a layer no rank
-        # had a token for is skipped on the device (has_grad, summed over ranks)
-        deferred = has_moe and dp.world > 1
-        names = list(wrapped)
-        has_grad = torch.zeros(len(names), dtype=torch.int32, device=device) if deferred else None
         name_of = {id(wl): n for n, wl in wrapped.items()}
 
         def update_layer(wl, grad_flag=None):
@@ -512,8 +513,12 @@ class SignRoundQuantizer:
             kw = dict(best_v=bv["value"], best_min=bv.get("min_scale"), best_max=bv["max_scale"], flag=flag, it_dev=it_dev,
                       clamp_hi=clamp_hi, init_scale=wl.init_scale, has_grad=grad_flag)
             args = (wl.spec, wl.weight, wl.value, wl.min_scale, wl.max_scale, wl.weight_min, wl.weight_max, wl.weight_global_scale)
-            if dp.world == 1:
-                ops.fq_update(*args, wl.gq, wl.wq, lr_tab, **kw)
+            owned = ep_owned.get(id(wl))
+            if dp.world == 1 or owned is not None:
+                # one GPU, or an expert layer under expert parallelism: its owner saw every token routed to it, so the
+                # gradient is complete locally (no exchange); the other ranks leave it alone
+                if owned is None or owned:
+                    ops.fq_update(*args, wl.gq, wl.wq, lr_tab, **kw)
                 return
             comm.wait_stream(compute_stream())                      # this layer's dWq and dX GEMMs are enqueued
             with torch.cuda.stream(comm):
@@ -527,7 +532,7 @@ class SignRoundQuantizer:
                     dp.all_gather_(wl.wq, wl.wq[r0:r1])
 
         for wl in wrapped.values():
-            wl.on_grad = None if deferred else update_layer
+            wl.on_grad = update_layer
 
         def iteration(last: bool):
             ops.sched_load(idx_dev, inv_tab, it_dev, lbs, cur32, cur64, cur_inv)
@@ -566,14 +571,6 @@ class SignRoundQuantizer:
             else:
                 bookkeeping()
             pred.backward(dpred.view_as(pred).to(pred.dtype))
-            if deferred:
-                has_grad.copy_(torch.tensor([1 if wrapped[n].got_grad else 0 for n in names], dtype=torch.int32), non_blocking=True)
-                for n in names:
-                    if not wrapped[n].got_grad:
-                        wrapped[n].gq.zero_()
-                dp.all_reduce_(has_grad)
-                for i, n in enumerate(names):
-                    update_layer(wrapped[n], has_grad[i:i + 1])
             if dp.world > 1:
                 compute_stream().wait_stream(comm)
             ops.iter_advance(it_dev)
@@ -583,7 +580,7 @@ class SignRoundQuantizer:
             # that also serve as warm-up) it is captured once -- forward, backward, the per-layer collectives on the
             # communication stream and the fused updates -- and replayed.
             n_eager = min(iters, 2)
-            use_graph = self.use_cuda_graph and not self.not_use_best_mse and iters > n_eager + 1 and not has_moe
+            use_graph = self.use_cuda_graph and not self.not_use_best_mse and iters > n_eager + 1
             graph = None
             if use_graph:
                 side = torch.cuda.Stream(device=device)
@@ -620,8 +617,14 @@ class SignRoundQuantizer:
         for wl in wrapped.values():
             wl.on_grad = None
         if dp.world > 1:            # every rank snapshotted its own row shard: rebuild the full best parameters
+            import torch.distributed as dist
+            for m in moe_mods:      # expert layers: the owner's best parameters go to everybody
+                for e in range(m.num_experts):
+                    for pj in ("gate_proj", "up_proj", "down_proj"):
+                        for t in best_of[name_of[id(m.layer(e, pj))]].values():
+                            dist.broadcast(t, src=m.owner_of(e), group=dp.group)
             for n, wl in wrapped.items():
-                if shards[n] is None:
+                if shards[n] is None or id(wl) in ep_owned:
                     continue
                 r0, r1 = shards[n]
                 kp, gpr = wl.spec.kpad, wl.spec.kpad // wl.spec.group_size
@@ -638,6 +641,8 @@ class SignRoundQuantizer:
             res.best_iter, res.best_loss = iters - 1, res.losses[-1]
         with torch.no_grad():
             self.unwrapper_block(block, wrapped, arena)
+        for m in moe_mods:
+            m.release()
         return {n: arena.best_views(n) for n in wrapped}
 
 

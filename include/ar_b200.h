@@ -117,6 +117,43 @@ int ar_gemm_bf16(const void* a, const void* b, void* d, int m, int n, int k, int
                  int64_t lda, int64_t ldb, int64_t ldd, const void* bias_bf16, void* stream);
 
 /*
+ * Grouped (ragged per-expert) bf16 GEMM on tcgen05 for un-fused MoE experts -- replaces the per-expert python loop of
+ * auto_round/modeling/fused_moe/moe_experts_interface.py:173-260 (`_run_experts_with_routes`).  Tiles are resolved through the
+ * device-side tables written by ar_moe_route in the same stream, so the launch is static (CUDA-graph capturable):
+ *   mode 1 (GROUP_M)  D[rows, n] = A[rows, k] · B_eᵀ,  e = expert of each 256-row tile (table: {m0, expert} x *num).
+ *                     b_mn_major = 0: B stacked [num_groups * group_rows, k], group_rows = n            (forward)
+ *                     b_mn_major = 1: B stored  [num_groups * group_rows, n], group_rows = k: the reduction runs over the
+ *                                     expert's rows                                                      (grad-in)
+ *   mode 2 (GROUP_K)  for every ACTIVE expert (table: {expert, k_off, k_len} x *num):
+ *                     D_e[group_rows, n] = A[k_off : k_off + k_len, :group_rows]ᵀ · B[k_off : k_off + k_len, :n]
+ *                     A stored [rows, group_rows], B stored [rows, n], D stacked [num_groups * group_rows, n]   (grad-w)
+ * rows = padded row capacity of the sorted token layout (multiple of 256); max_entries bounds *num (grid sizing only).
+ */
+int ar_gemm_bf16_grouped(const void* a, const void* b, void* d, int mode, int rows, int n, int k, int a_mn_major, int b_mn_major,
+                         int64_t lda, int64_t ldb, int64_t ldd, int group_rows, int num_groups, const int32_t* table,
+                         const int32_t* num, int max_entries, void* stream);
+
+/*
+ * MoE routing on the device (csrc/ar_moe.cu): expert_ids int64 [pairs = tokens * topk] -> the (token, slot) pairs sorted by
+ * expert with every expert's segment padded to 256 rows.  Only experts [e_begin, e_begin + e_local) get rows (expert-parallel
+ * ownership; e_local <= 32).  Outputs (int32, device): counts[e_local], offsets[e_local + 1], row_of_pair[pairs] (-1 = not
+ * local), pair_of_row[max_rows] (-1 = padding), the GROUP_M table mtab[2 * max_rows / 256] + *num_mt and the GROUP_K table
+ * ktab[3 * e_local] + *num_active.  max_rows: multiple of 256, >= pairs + 255 * e_local.
+ *   ar_moe_gather   out[row, :] = x[pair_of_row[row] / topk, :] (* pair_w[pair], bf16 product) ; padding rows = 0
+ *   ar_moe_combine  out[token, :] = bf16(sum_slot bf16(d[row, :] * pair_w[pair]) (+ d2[row, :]))   pair_w NULL: plain sum
+ *   ar_moe_rowdot   dw[pair] = bf16(<g[token, :], d[row, :]>)                                      (0 without a row)
+ */
+int ar_moe_route(const int64_t* expert_ids, int pairs, int e_begin, int e_local, int max_rows, int32_t* counts, int32_t* offsets,
+                 int32_t* row_of_pair, int32_t* pair_of_row, int32_t* mtab, int32_t* num_mt, int32_t* ktab, int32_t* num_active,
+                 void* stream);
+int ar_moe_gather(const void* x_bf16, const int32_t* pair_of_row, const void* pair_w_bf16, int topk, int rows, int cols,
+                  void* out_bf16, void* stream);
+int ar_moe_combine(const void* d_bf16, const void* d2_bf16, const int32_t* row_of_pair, const void* pair_w_bf16, int tokens,
+                   int topk, int cols, void* out_bf16, void* stream);
+int ar_moe_rowdot(const void* g_bf16, const void* d_bf16, const int32_t* row_of_pair, int pairs, int topk, int cols,
+                  void* dw_bf16, void* stream);
+
+/*
  * Fake-quant linear, forward:  Y[T,N] = X[T,K] · qdq(W)ᵀ (+bias).  wq_scratch (bf16 [N,K]) receives the
  * fake-quant weight once per call (reused by ar_fq_linear_bwd_dx).  = WrapperLinear.forward,
  * auto_round/wrapper.py:517-565.

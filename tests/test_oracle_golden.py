@@ -296,12 +296,13 @@ def test_tune_block_other_architectures_match_reference_bit_exact(golden_dir, ar
 def test_tune_block_mixtral_moe_matches_reference_bit_exact(golden_dir):
     """BASELINE.json config 5 (Mixtral, MXFP4 weight-only) on a tiny 4-expert block: the reference un-fuses the fused 3-D
     expert parameters into per-expert linears (modeling/fused_moe/moe_experts_interface.py:173-260).  The block here is built
-    with the PRODUCT's host-side un-fusing (auto_round_b200/moe.py, pure torch), so a bit-exact replay of the reference's
-    8 iterations pins that module and the oracle loop on ragged expert batches (experts that see no token get no update)."""
+    with the oracle's restatement of that un-fusing and expert loop (oracle/moe_loop.py), so a bit-exact replay of the
+    reference's 8 iterations pins it and the oracle loop on ragged expert batches (experts that see no token get no update);
+    the product's grouped tcgen05 path (auto_round_b200/moe.py) is checked against it on the GPU (tests/test_gpu_moe.py)."""
     from transformers import MixtralConfig
     from transformers.models.mixtral.modeling_mixtral import MixtralDecoderLayer
 
-    from auto_round_b200.moe import unfuse_experts
+    from oracle.moe_loop import unfuse_experts_cpu as unfuse_experts
 
     rec = _load(golden_dir, "block_mixtral_mxfp4.pt")
     sc = S.LayerScheme(4, 32, True, "mx_fp")
