@@ -34,7 +34,7 @@ SIGNATURES = {
     "ar_qdq_mx_fp4_fwd": [_QS, _P, _P, _P, _P, _P, _P],
     "ar_qdq_nv_fp4_fwd": [_QS, _P, _P, _P, _P, _P, _P, _P],
     "ar_gemm_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _P, _P],
-    "ar_gemm_bf16_grouped": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _L, _L, _L, _I, _I, _P, _P, _I, _P],
+    "ar_gemm_bf16_grouped": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _L, _L, _L, _I, _I, _P, _P, _I, _I, _P],
     "ar_moe_route": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "ar_moe_gather": [_P, _P, _P, _I, _I, _I, _P, _P],
     "ar_moe_combine": [_P, _P, _P, _P, _I, _I, _I, _P, _P],

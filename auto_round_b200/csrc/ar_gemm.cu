@@ -298,7 +298,7 @@ struct GemmParams {
   int m, n, k;                    // logical problem: D[m,n] = A[m,k] B[n,k]^T
   GroupDesc grp;
   // host-only (grouped launches): extents of the tensor maps when they differ from the logical problem, and the tile bound
-  int b_rows_map, b_k_map, d_rows_map, max_tiles;
+  int a_rows_map, b_rows_map, b_k_map, d_rows_map, max_tiles;
   int m_tiles, n_tiles;
   const uint16_t* bias;           // EPI_STORE, optional [n]
   unsigned int* tile_ctr;         // dynamic tile scheduler: ticket counter of this launch (0 at launch, reset to 0 at exit)
@@ -824,8 +824,9 @@ static int launch_cg(const void* a, const void* b, void* d, int m, int n, int k,
   }
   CUtensorMap ma, mb, md;
   int rc;
-  if (!A_MN) rc = make_map(&ma, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, 64, BLOCK_M);   // stored [m, k]
-  else rc = make_map(&ma, a, (uint64_t)m, (uint64_t)k, (uint64_t)lda, 64, BLOCK_K);          // stored [k, m]
+  const uint64_t a_rows = base.a_rows_map > 0 ? (uint64_t)base.a_rows_map : (uint64_t)m;
+  if (!A_MN) rc = make_map(&ma, a, (uint64_t)k, a_rows, (uint64_t)lda, 64, BLOCK_M);         // stored [m, k]
+  else rc = make_map(&ma, a, a_rows, (uint64_t)k, (uint64_t)lda, 64, BLOCK_K);               // stored [k, m]
   if (rc) return rc;
   const uint64_t b_rows = base.b_rows_map > 0 ? (uint64_t)base.b_rows_map : (uint64_t)n;
   const uint64_t b_k = base.b_k_map > 0 ? (uint64_t)base.b_k_map : (uint64_t)k;
@@ -907,7 +908,7 @@ extern "C" int ar_gemm_bf16(const void* a, const void* b, void* d, int m, int n,
 
 extern "C" int ar_gemm_bf16_grouped(const void* a, const void* b, void* d, int mode, int rows, int n, int k, int a_mn, int b_mn,
                                     int64_t lda, int64_t ldb, int64_t ldd, int group_rows, int num_groups,
-                                    const int32_t* table, const int32_t* num, int max_entries, void* stream) {
+                                    const int32_t* table, const int32_t* num, int max_entries, int a_features, void* stream) {
   AR_REQUIRE(a && b && d && table && num && rows > 0 && n > 0 && k > 0 && group_rows > 0 && num_groups > 0 && max_entries > 0,
              AR_E_BADARG, "bad grouped gemm args");
   AR_REQUIRE(mode == GROUP_M || mode == GROUP_K, AR_E_BADARG, "mode must be 1 (GROUP_M) or 2 (GROUP_K)");
@@ -935,7 +936,10 @@ extern "C" int ar_gemm_bf16_grouped(const void* a, const void* b, void* d, int m
   // GROUP_K: D_e[n_out = `n`... ] -- here the logical problem per active expert is D[m = group_rows, n] = A^T B over that
   // expert's rows; A stored [rows, m] and B stored [rows, n] (both MN-major), D stacked [G * group_rows, n]
   AR_REQUIRE(a_mn && b_mn, AR_E_UNSUPPORTED, "GROUP_K: A and B must be MN-major (stored [rows, features])");
-  AR_REQUIRE(group_rows % 256 == 0, AR_E_UNSUPPORTED, "GROUP_K: output rows per expert must be a multiple of 256");
+  AR_REQUIRE(group_rows % 256 == 0, AR_E_UNSUPPORTED,
+             "GROUP_K: the row pitch of the stacked output must be a multiple of 256 (pad the per-expert slab)");
+  AR_REQUIRE(a_features > 0 && a_features <= group_rows, AR_E_BADARG, "GROUP_K: a_features must be in (0, group_rows]");
+  p.a_rows_map = a_features;                 // feature columns of A beyond the real count are zero-filled by TMA
   p.grp.d_group_rows = group_rows;
   p.d_rows_map = group_rows * num_groups;
   p.max_tiles = max_entries * (group_rows / 256) * ((n + 255) / 256);

@@ -192,10 +192,11 @@ class GroupedExperts(nn.Module):
         for p in PROJS:
             n, k = self.layer(0, p).weight.shape
             self._fq[p] = torch.empty(self.num_experts, n, k, dtype=torch.bfloat16, device=dev)
-            self._grads[p] = torch.zeros(self.num_experts, n, k, dtype=torch.bfloat16, device=dev)
+            pitch = (n + 255) // 256 * 256          # row pitch of an expert's gradient slab: whole 256-row GEMM tiles
+            self._grads[p] = torch.zeros(self.num_experts, pitch, k, dtype=torch.bfloat16, device=dev)
             for e in range(self.num_experts):
                 wl = self.layer(e, p)
-                wl.wq, wl.gq = self._fq[p][e], self._grads[p][e]
+                wl.wq, wl.gq = self._fq[p][e], self._grads[p][e, :n]
         self.anchor = torch.zeros((), dtype=torch.float32, device=dev, requires_grad=True)
         self.ep = ep if (ep is not None and ep.world > 1) else None
         if self.ep is not None and self.num_experts % self.ep.world:

@@ -411,19 +411,23 @@ def gemm_grouped_m(a, b_stack, route: MoeRoute, n, k, b_mn_major=False, out=None
     group_rows = k if b_mn_major else n
     _check(_lib.load().ar_gemm_bf16_grouped(_p(a), _p(b_stack), _p(out), 1, rows, n, k, 0, int(b_mn_major), a.stride(0),
                                             b_stack.stride(1), out.stride(0), group_rows, e, _p(route.mtab), _p(route.num_mt),
-                                            rows // 256, _stream()), "ar_gemm_bf16_grouped")
+                                            rows // 256, 0, _stream()), "ar_gemm_bf16_grouped")
     return out
 
 
 def gemm_grouped_k(dy, x, route: MoeRoute, out_stack):
-    """GROUP_K: out_stack[e] ([E, n_out, k_out]) = dy[rows_e, :n_out]ᵀ · x[rows_e, :k_out] for every expert with tokens."""
+    """GROUP_K: out_stack[e, :n_out] = dy[rows_e, :n_out]ᵀ · x[rows_e, :k_out] for every expert with tokens.  out_stack is
+    [E, pitch, k_out] with pitch = n_out rounded up to 256 (rows n_out.. of a slab are scratch)."""
     _want(dy, torch.bfloat16, "dy")
     _want(x, torch.bfloat16, "x")
     _want(out_stack, torch.bfloat16, "out")
-    e, n_out, k_out = out_stack.shape
+    e, pitch, k_out = out_stack.shape
+    n_out = dy.shape[1]
+    if pitch % 256 or pitch < n_out or not out_stack.is_contiguous():
+        raise ValueError("out_stack must be contiguous [E, pitch, k_out] with pitch a multiple of 256 >= dy.shape[1]")
     _check(_lib.load().ar_gemm_bf16_grouped(_p(dy), _p(x), _p(out_stack), 2, route.max_rows, k_out, route.max_rows, 1, 1,
-                                            dy.stride(0), x.stride(0), out_stack.stride(1), n_out, e, _p(route.ktab),
-                                            _p(route.num_active), route.e_local, _stream()), "ar_gemm_bf16_grouped")
+                                            dy.stride(0), x.stride(0), k_out, pitch, e, _p(route.ktab),
+                                            _p(route.num_active), route.e_local, n_out, _stream()), "ar_gemm_bf16_grouped")
     return out_stack
 
 

@@ -60,7 +60,20 @@ CONFIGS = {
         scheme=dict(scheme="NVFP4", act_bits=16, act_data_type="float"), spec=("nv_fp4", 4, 16), linears=_QWEN_LIN,
         workload="Qwen2-7B NVFP4 weight-only g16 iters=%d nsamples=128 seqlen=2048 batch=8 on %dxB200"),
 }
+_MIXTRAL_LIN = [("q", 4096, 4096, False), ("k", 1024, 4096, False), ("v", 1024, 4096, False), ("o", 4096, 4096, True),
+                # top-2 of 8 experts: per token two gate / up / down projections are active (the FLOP count of a step)
+                ("e0.gate", 14336, 4096, True), ("e0.up", 14336, 4096, True), ("e0.down", 4096, 14336, True),
+                ("e1.gate", 14336, 4096, True), ("e1.up", 14336, 4096, True), ("e1.down", 4096, 14336, True)]
+CONFIGS["mixtral_mxfp4"] = dict(
+    metric="Mixtral-8x7B MXFP4 (weight-only) calib wall-clock (s) @200 iters", model="mixtral_8x7b", n_blocks=32, iters=200,
+    scheme=dict(scheme="MXFP4", act_bits=16), spec=("mx_fp4", 4, 32), linears=_MIXTRAL_LIN,
+    p_block=4096 * 4096 * 2 + 1024 * 4096 * 2 + 8 * 3 * 14336 * 4096,
+    workload="Mixtral-8x7B MXFP4 weight-only g32 iters=%d nsamples=128 seqlen=2048 batch=8 on %dxB200")
 MODELS = {
+    "mixtral_8x7b": ("MixtralConfig", "MixtralForCausalLM", dict(hidden_size=4096, intermediate_size=14336, num_attention_heads=32,
+                                                              num_key_value_heads=8, vocab_size=32000, rope_theta=1000000.0,
+                                                              rms_norm_eps=1e-5, max_position_embeddings=32768,
+                                                              num_local_experts=8, num_experts_per_tok=2)),
     "llama3_8b": ("LlamaConfig", "LlamaForCausalLM", dict(hidden_size=4096, intermediate_size=14336, num_attention_heads=32,
                                                          num_key_value_heads=8, vocab_size=128256, rope_theta=500000.0,
                                                          rms_norm_eps=1e-5, max_position_embeddings=8192)),
@@ -195,7 +208,8 @@ def line_config(cfg, iters, world, n_measured):
             "step": "one decoder block through the tuning span (ref fwd, %d sign-SGD iters, q fwd, unwrap, pack)" % iters,
             "value_is": "ms_per_step x %d blocks (identical shapes)%s" % (cfg["n_blocks"], "" if n_measured != cfg["n_blocks"] else "; measured over all"),
             "parallelism": "dp%d (calibration samples sharded; per layer: reduce-scatter of the bf16 dWq, row-sharded fused update, "
-                           "all-gather of the next fake-quant weight, overlapped with the backward)" % world,
+                           "all-gather of the next fake-quant weight, overlapped with the backward%s)"
+                           % (world, "; MoE experts: expert-parallel ownership, all-gather of tokens + reduce-scatter of outputs" if "mixtral" in cfg["model"] else ""),
             "l2": "inputs larger than L2 (per-iteration working set 3.4 GB >> 126 MB)"}
 
 
@@ -272,7 +286,7 @@ def run_ours(args):
     value_s = ms_per_step * nb / 1e3
     e2e_s = (e2e_ms / K) * nb / 1e3
     flops_step = flops_per_step(cfg, iters)
-    p_block = sum(n * k for _, n, k, _ in cfg["linears"])
+    p_block = cfg.get("p_block") or sum(n * k for _, n, k, _ in cfg["linears"])
     hidden = MODELS[cfg["model"]][2]["hidden_size"]
     h2d = (p_block + 2 * hidden) * 2                                # bf16 linears + the two RMSNorm weights
     bits, g = cfg["spec"][1], cfg["spec"][2]
@@ -301,10 +315,13 @@ def run_ours(args):
         line["dp_probe"] = dp_probe
     if world == 1:
         roof = gemm_roofline(dev, pk, cfg)
-        try:
-            roof["in_context"] = iteration_timeline(dev, pk, cfg, args.config)
-        except Exception as e:  # noqa: BLE001 -- a diagnostic, never the value
-            roof["in_context"] = {"error": repr(e)[:200]}
+        if "mixtral" in cfg["model"]:
+            roof["note"] = "dense replay of the ACTIVE launch mix (top-2 experts at T tokens each); the run itself uses the grouped kernels"
+        else:
+            try:
+                roof["in_context"] = iteration_timeline(dev, pk, cfg, args.config)
+            except Exception as e:  # noqa: BLE001 -- a diagnostic, never the value
+                roof["in_context"] = {"error": repr(e)[:200]}
         line["roofline"] = roof
         if orig_block0 is not None:
             try:
@@ -513,12 +530,16 @@ def mse_vs_reference(ar, model, orig_block0, cfg, iters, dev, line):
     osc = S.LayerScheme(bits, g, name != "int_asym", {"int_sym": "int", "int_asym": "int", "mx_fp4": "mx_fp", "nv_fp4": "nv_fp"}[name])
     # RTN (iteration-0 parameters): the floor both tuners start from
     rtn = copy.deepcopy(orig_block0).to(dev)
+    from oracle.moe_loop import unfuse_experts_cpu as _unfuse
+    _unfuse(rtn)
     wr = S.wrap_block(rtn, lambda n, m: osc)
     S.unwrap_block(rtn, wr, {})
     mse_rtn = mse(fwd_all(rtn), refs)
     del rtn, wr
     # the reference's algorithm, eager on this GPU, same batches as block 0 of the timed run
     oblk = copy.deepcopy(orig_block0).to(dev)
+    from oracle.moe_loop import unfuse_experts_cpu
+    unfuse_experts_cpu(oblk)                         # MoE: the reference's per-expert loop (no-op for dense blocks)
     batches = ar.block_results[0]["batches"]
     nv = None
     if name == "nv_fp4":
@@ -557,17 +578,20 @@ def mse_vs_reference(ar, model, orig_block0, cfg, iters, dev, line):
 
 # ----------------------------------------------------------------------------------------------- reference arm (CPU)
 def _cpu_block(cfg):
+    import importlib
+
     import transformers
 
     cfg_cls, _, kw = MODELS[cfg["model"]]
     c = getattr(transformers, cfg_cls)(num_hidden_layers=1, **kw)
     c._attn_implementation = "sdpa"
     torch.manual_seed(0)
-    mod = __import__("transformers.models.%s.modeling_%s" % (("llama", "llama") if cfg["model"].startswith("llama") else ("qwen2", "qwen2")),
-                     fromlist=["x"])
-    layer_cls = getattr(mod, "LlamaDecoderLayer" if cfg["model"].startswith("llama") else "Qwen2DecoderLayer")
-    rot_cls = getattr(mod, "LlamaRotaryEmbedding" if cfg["model"].startswith("llama") else "Qwen2RotaryEmbedding")
-    return c, layer_cls(c, 0).to(torch.bfloat16).eval(), rot_cls(c)
+    fam, cls = {"llama3_8b": ("llama", "Llama"), "qwen2_7b": ("qwen2", "Qwen2"), "mixtral_8x7b": ("mixtral", "Mixtral")}[cfg["model"]]
+    mod = importlib.import_module(f"transformers.models.{fam}.modeling_{fam}")
+    blk = getattr(mod, cls + "DecoderLayer")(c, 0).to(torch.bfloat16).eval()
+    from oracle.moe_loop import unfuse_experts_cpu
+    unfuse_experts_cpu(blk)                          # MoE: the reference's per-expert linears + loop (no-op otherwise)
+    return c, blk, getattr(mod, cls + "RotaryEmbedding")(c)
 
 
 def cpu_steps(cfg, steps, warmup, budget_s, threads=None):

@@ -126,12 +126,14 @@ int ar_gemm_bf16(const void* a, const void* b, void* d, int m, int n, int k, int
  *                                     expert's rows                                                      (grad-in)
  *   mode 2 (GROUP_K)  for every ACTIVE expert (table: {expert, k_off, k_len} x *num):
  *                     D_e[group_rows, n] = A[k_off : k_off + k_len, :group_rows]ᵀ · B[k_off : k_off + k_len, :n]
- *                     A stored [rows, group_rows], B stored [rows, n], D stacked [num_groups * group_rows, n]   (grad-w)
- * rows = padded row capacity of the sorted token layout (multiple of 256); max_entries bounds *num (grid sizing only).
+ *                     A stored [rows, a_features], B stored [rows, n], D stacked [num_groups * group_rows, n] with
+ *                     group_rows = a_features rounded up to 256 (the row pitch of an expert's output slab)   (grad-w)
+ * rows = padded row capacity of the sorted token layout (multiple of 256); max_entries bounds *num (grid sizing only);
+ * a_features is ignored in mode 1.
  */
 int ar_gemm_bf16_grouped(const void* a, const void* b, void* d, int mode, int rows, int n, int k, int a_mn_major, int b_mn_major,
                          int64_t lda, int64_t ldb, int64_t ldd, int group_rows, int num_groups, const int32_t* table,
-                         const int32_t* num, int max_entries, void* stream);
+                         const int32_t* num, int max_entries, int a_features, void* stream);
 
 /*
  * MoE routing on the device (csrc/ar_moe.cu): expert_ids int64 [pairs = tokens * topk] -> the (token, slot) pairs sorted by

@@ -119,7 +119,7 @@ def test_grouped_backward_matches_autograd_of_the_loop():
     for i in range(e):
         for p in PROJS:
             want = getattr(getattr(ref, str(i)), p).weight.grad
-            got = mod.grad_stack(p)[i]
+            got = mod.layer(i, p).gq
             if i == 2:
                 assert want is None or float(want.abs().max()) == 0.0            # no token -> no gradient ...
                 assert float(got.abs().max()) == 0.0                              # ... and the buffer is left untouched
