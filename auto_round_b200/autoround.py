@@ -464,7 +464,7 @@ class AutoRound:
 
         quantizer = SignRoundQuantizer(self.scheme, iters=self.iters, batch_size=self.batch_size, amp_dtype=self.amp_dtype,
                                        layer_config=self.layer_config, dp=self.dp, enable_alg_ext=self.enable_alg_ext,
-                                       **self.sign_kw)
+                                       gradient_accumulate_steps=self.gradient_accumulate_steps, **self.sign_kw)
         self.quantizer = quantizer
         t0 = time.time()                                                  # orchestrator.py:631
         q_inputs = None

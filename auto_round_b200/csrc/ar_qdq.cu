@@ -324,7 +324,11 @@ __device__ __forceinline__ float sign_step(float p, float lr, float g) {
 template <class Ctx, int G, bool IS_FP4>
 __global__ void __launch_bounds__(kThreads) fq_update_kernel(QArgs a, UpdArgs u) {
   constexpr int LPG = G / 8;
-  if (u.has_grad != nullptr && *u.has_grad == 0) return;
+  // a layer without a gradient this iteration (an expert no token was routed to) is not stepped, but it still takes part
+  // in the best-parameter snapshot: collect_best_params clones EVERY parameter (compressors/utils.py:205-217)
+  const bool no_grad = (u.has_grad != nullptr) && (*u.has_grad == 0);
+  const bool snap_any = (u.flag != nullptr) && (*u.flag != 0) && (u.best_v != nullptr);
+  if (no_grad && !snap_any) return;
   const int cpr = a.kpad / 8;
   const int64_t total = (int64_t)(u.row1 - u.row0) * cpr;
   const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -336,7 +340,18 @@ __global__ void __launch_bounds__(kThreads) fq_update_kernel(QArgs a, UpdArgs u)
   const bool vec = (a.k % 8) == 0;
   const int iter = u.it_ptr ? *u.it_ptr : u.iter;
   const float lr_v = u.lr_table[2 * iter], lr_s = u.lr_table[2 * iter + 1];
-  const bool snap = (u.flag != nullptr) && (*u.flag != 0) && (u.best_v != nullptr);
+  const bool snap = snap_any;
+  if (no_grad) {                                     // snapshot only
+    if (!valid) return;
+    const int64_t vo = (int64_t)n * a.kpad + k0;
+    *reinterpret_cast<float4*>(u.best_v + vo) = *reinterpret_cast<const float4*>(u.v + vo);
+    *reinterpret_cast<float4*>(u.best_v + vo + 4) = *reinterpret_cast<const float4*>(u.v + vo + 4);
+    if ((k0 % G) == 0) {
+      if (u.best_mx) u.best_mx[gidx] = u.mx[gidx];
+      if (u.best_mn && u.mn) u.best_mn[gidx] = u.mn[gidx];
+    }
+    return;
+  }
   float w[8], v[8], g[8];
   load_w8(a.w, (int64_t)n * a.k, k0, a.k, vec, w);
   load_w8(u.gq, (int64_t)(n - u.gq_row0) * a.k, k0, a.k, vec, g);

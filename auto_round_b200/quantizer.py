@@ -91,7 +91,7 @@ class TuneArena:
         self.numel = off
         self.params = torch.zeros(off, dtype=torch.float32, device=device)
         self.params[self.clamp_begin:] = 1.0          # min/max_scale start at 1, V at 0 (wrapper.py:184-190)
-        self.best = torch.zeros(off, dtype=torch.float32, device=device)
+        self.best = self.params.clone()               # (a layer that never gets a gradient keeps its initial parameters)
         self.gq_views, goff = {}, 0
         for name, spec in specs.items():
             self.gq_views[name] = (goff, spec.n * spec.k, (spec.n, spec.k))
@@ -260,8 +260,7 @@ class SignRoundQuantizer:
         self.use_cuda_graph = use_cuda_graph
         self.fuse_block_ops = fuse_block_ops
         self.grad_dtype = grad_dtype        # kept for API compatibility: the weight gradient is bf16 (autograd of F.linear)
-        if gradient_accumulate_steps != 1:
-            raise NotImplementedError("gradient_accumulate_steps != 1 (reference default is 1)")
+        self.gradient_accumulate_steps = max(1, int(gradient_accumulate_steps or 1))
         self.last_result: Optional[TuneResult] = None
         self.last_arena = None
 
@@ -434,15 +433,20 @@ class SignRoundQuantizer:
 
         # ---- schedules drawn up-front (same python-random stream as the reference's IndexSampler)
         iters = self.iters
-        gbs = min(nsamples, self.batch_size)
+        # gradient_accumulate_steps = A > 1 (quantizer.py:437-452): an iteration draws batch_size * A samples and runs them
+        # as A micro-batches of batch_size; MSELoss(reduction="sum"), gradients accumulate, ONE sign-SGD step
+        accum = self.gradient_accumulate_steps
+        mbs = min(nsamples, self.batch_size)
+        gbs = min(nsamples, mbs * accum)
+        accum = (gbs + mbs - 1) // mbs
         sampler = kwargs.get("sampler") or IndexSampler(nsamples, gbs)
         batches = [list(sampler.next_batch()) for _ in range(iters)]
         res.batches = batches
-        local = [dp.shard(b) for b in batches]
-        lbs = len(local[0])
-        if lbs == 0:
-            raise RuntimeError(f"batch_size {gbs} cannot be sharded over {dp.world} ranks")
-        idx_dev = torch.tensor(local, dtype=torch.int32, device=device)
+        micro = [[dp.shard(b[j * mbs:(j + 1) * mbs]) for j in range(accum)] for b in batches]
+        lbs = len(micro[0][0])
+        if lbs == 0 or any(len(m) != lbs for it_m in micro for m in it_m):
+            raise RuntimeError(f"micro-batches of {mbs} samples (global batch {gbs}) cannot be sharded evenly over {dp.world} ranks")
+        idx_dev = torch.tensor(micro, dtype=torch.int32, device=device).reshape(iters, accum * lbs)
         bits_all = {wl.scheme.bits for wl in wrapped.values()}
         lr0 = self.compute_lr(min(bits_all))
         mm_lr0 = float(self.minmax_lr) if self.minmax_lr is not None else lr0
@@ -454,18 +458,21 @@ class SignRoundQuantizer:
         state = torch.zeros(4, dtype=torch.float64, device=device)
         flag = torch.zeros(1, dtype=torch.int32, device=device)
         hist = torch.zeros(iters, dtype=torch.float32, device=device)
-        inv_numel = 1.0 / float(gbs * seq * hidden)               # MSELoss('mean') over the GLOBAL batch
+        # MSELoss('mean') over the GLOBAL batch; with accumulation the reference switches to reduction='sum'
+        inv_numel = 1.0 / float(gbs * seq * hidden) if accum == 1 else 1.0
         x_buf = torch.empty((lbs,) + tuple(x_all.shape[1:]), dtype=x_all.dtype, device=device)
         ref_buf = torch.empty_like(x_buf)
 
         # ---- device-side schedule: iteration counter, current batch indices, 1/num_elm of the current batch
         it_dev = torch.zeros(1, dtype=torch.int32, device=device)
-        cur32 = torch.zeros(lbs, dtype=torch.int32, device=device)
-        cur64 = torch.zeros(lbs, dtype=torch.int64, device=device)
+        cur32 = torch.zeros(accum * lbs, dtype=torch.int32, device=device)
+        cur64 = torch.zeros(accum * lbs, dtype=torch.int64, device=device)
         cur_inv = torch.ones(1, dtype=torch.float64, device=device)
         if token_masks is not None:
             inv_tab = torch.tensor([1.0 / max(1, sum(valid_per_sample[i] for i in b)) for b in batches],
                                    dtype=torch.float64, device=device)
+        elif accum > 1:           # num_elm = elements of the first global batch's inputs (quantizer.py:445-449)
+            inv_tab = torch.full((iters,), 1.0 / float(gbs * seq * hidden), dtype=torch.float64, device=device)
         else:
             inv_tab = torch.ones(iters, dtype=torch.float64, device=device)
 
@@ -534,43 +541,71 @@ class SignRoundQuantizer:
         for wl in wrapped.values():
             wl.on_grad = update_layer
 
+        # gradient accumulation: fp32 sums of the micro-batches' bf16 dWq (the reference accumulates V.grad in fp32; dV is
+        # linear in dWq for fixed parameters), rounded to bf16 once for the fused update after the last micro-batch
+        acc_state = {"first": True, "final": True}
+        gq_acc = {}
+        if accum > 1:
+            if moe_mods:
+                raise NotImplementedError("gradient_accumulate_steps > 1 with grouped MoE experts")
+            if outlier_loss:
+                raise NotImplementedError("gradient_accumulate_steps > 1 with the outlier-suppressed loss (enable_alg_ext, bits < 4)")
+            gq_acc = {n: torch.zeros(wl.spec.n, wl.spec.k, dtype=torch.float32, device=device) for n, wl in wrapped.items()}
+
+            def accumulate_then_update(wl, grad_flag=None):
+                a = gq_acc[name_of[id(wl)]]
+                if acc_state["first"]:
+                    a.copy_(wl.gq)
+                else:
+                    a.add_(wl.gq)
+                if acc_state["final"]:
+                    wl.gq.copy_(a)
+                    update_layer(wl, grad_flag)
+
+            for wl in wrapped.values():
+                wl.on_grad = accumulate_then_update
+
         def iteration(last: bool):
-            ops.sched_load(idx_dev, inv_tab, it_dev, lbs, cur32, cur64, cur_inv)
-            ops.gather_rows(x_all, cur32, out=x_buf)
-            ops.gather_rows(ref_all, cur32, out=ref_buf)
-            kw = dict(static_kw)
-            for key, val in per_sample_kw.items():
-                kw[key] = val.index_select(0, cur64)
-            mask_rows = None
-            if token_masks is not None:
-                mask_rows = token_masks.index_select(0, cur64).reshape(-1)
+            ops.sched_load(idx_dev, inv_tab, it_dev, accum * lbs, cur32, cur64, cur_inv)
             for wl in wrapped.values():
                 wl.got_grad = False
-            pred = self.block_forward(block, x_buf, kw)
-            pred2d = pred.reshape(-1, hidden)
-            if pred2d.dtype != torch.bfloat16:
-                pred2d = pred2d.to(torch.bfloat16)
-            pred2d, ref2d = pred2d.contiguous(), ref_buf.reshape(-1, hidden)
-            if outlier_loss:
-                dpred = ops.mse_outlier_fwd_bwd(pred2d, ref2d, mask_rows, 1000.0, loss_sum, outlier_scratch,
-                                                numel_global=gbs * seq * hidden if dp.world > 1 else None,
-                                                all_gather=dp.all_gather_, rank=dp.rank, world=dp.world)
-            else:
-                dpred = ops.mse_fwd_bwd(pred2d, ref2d, None if unmasked_loss else mask_rows, inv_numel, 1000.0, loss_sum)
+            for j in range(accum):
+                c32, c64 = cur32[j * lbs:(j + 1) * lbs], cur64[j * lbs:(j + 1) * lbs]
+                acc_state["first"], acc_state["final"] = (j == 0), (j == accum - 1)
+                ops.gather_rows(x_all, c32, out=x_buf)
+                ops.gather_rows(ref_all, c32, out=ref_buf)
+                kw = dict(static_kw)
+                for key, val in per_sample_kw.items():
+                    kw[key] = val.index_select(0, c64)
+                mask_rows = None
+                if token_masks is not None:
+                    mask_rows = token_masks.index_select(0, c64).reshape(-1)
+                pred = self.block_forward(block, x_buf, kw)
+                pred2d = pred.reshape(-1, hidden)
+                if pred2d.dtype != torch.bfloat16:
+                    pred2d = pred2d.to(torch.bfloat16)
+                pred2d, ref2d = pred2d.contiguous(), ref_buf.reshape(-1, hidden)
+                if outlier_loss:
+                    dpred = ops.mse_outlier_fwd_bwd(pred2d, ref2d, mask_rows, 1000.0, loss_sum, outlier_scratch,
+                                                    numel_global=gbs * seq * hidden if dp.world > 1 else None,
+                                                    all_gather=dp.all_gather_, rank=dp.rank, world=dp.world)
+                else:
+                    dpred = ops.mse_fwd_bwd(pred2d, ref2d, None if unmasked_loss else mask_rows, inv_numel, 1000.0, loss_sum)
 
-            def bookkeeping():                                      # loss -> best flag (read by every update kernel)
-                ops.best_update(loss_sum, inv_numel, 1.0, 0, state, flag, hist, inv_num_elm_dev=cur_inv, it_dev=it_dev)
-                if self.not_use_best_mse:
-                    flag.fill_(1 if last else 0)
+                def bookkeeping():                                  # loss -> best flag (read by every update kernel)
+                    ops.best_update(loss_sum, inv_numel, 1.0, 0, state, flag, hist, inv_num_elm_dev=cur_inv, it_dev=it_dev)
+                    if self.not_use_best_mse:
+                        flag.fill_(1 if last else 0)
 
-            if dp.world > 1:
-                comm.wait_stream(compute_stream())
-                with torch.cuda.stream(comm):
-                    dp.all_reduce_(loss_sum)                       # the best iteration is chosen on the GLOBAL loss
-                    bookkeeping()
-            else:
-                bookkeeping()
-            pred.backward(dpred.view_as(pred).to(pred.dtype))
+                if j == accum - 1:                                  # the iteration's loss is complete
+                    if dp.world > 1:
+                        comm.wait_stream(compute_stream())
+                        with torch.cuda.stream(comm):
+                            dp.all_reduce_(loss_sum)               # the best iteration is chosen on the GLOBAL loss
+                            bookkeeping()
+                    else:
+                        bookkeeping()
+                pred.backward(dpred.view_as(pred).to(pred.dtype))
             if dp.world > 1:
                 compute_stream().wait_stream(comm)
             ops.iter_advance(it_dev)

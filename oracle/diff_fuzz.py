@@ -190,6 +190,9 @@ def run_loops():
         ("custom_lr", dict(scheme="W2A16", group_size=32, sym=False, lr=0.01, minmax_lr=0.02), S.LayerScheme(2, 32, False, "int"),
          dict(lr=0.01, minmax_lr=0.02)),
         ("nvfp4_bs2", dict(scheme="NVFP4", act_bits=16, act_data_type="float"), S.LayerScheme(4, 16, True, "nv_fp"), dict()),
+        # gradient accumulation: 2 micro-batches of 2 per iteration, MSELoss('sum'), one step (quantizer.py:436-452)
+        ("accum2_bs2", dict(scheme="W4A16", group_size=32, gradient_accumulate_steps=2), S.LayerScheme(4, 32, True, "int"),
+         dict(gradient_accumulate_steps=2)),
     ]
     failures, cases = [], 0
     for tag, kw, sc, okw in configs:
@@ -203,6 +206,8 @@ def run_loops():
                                token_masks=masks, nv_global_scales=b["nv_gs"] or None, sampler=S.ReplaySampler(b["batches"]), **okw)
             nvalid = [sum(int(masks[i].sum()) for i in batch) for batch in b["batches"]]
             got = [l * n for l, n in zip(res.losses, nvalid)]
+            if okw.get("gradient_accumulate_steps", 1) != 1:       # the reference logs one (sum-reduced) loss per micro-batch
+                got = list(res.micro_losses)
             cases += 1
             if any(abs(a - e) > 1e-6 * abs(e) for a, e in zip(got, b["losses"])) or len(got) != len(b["losses"]):
                 failures.append(f"loop {tag} block {bi}: losses differ")

@@ -250,11 +250,12 @@ def block_forward(block, hidden, others: dict, amp=True, amp_dtype=torch.bfloat1
     return out[0] if isinstance(out, (tuple, list)) else out
 
 
-def masked_mse(pred, ref, mask):
-    """quantizer.py:142-156 -- MSELoss('mean') over ALL elements; masked tokens contribute zeros."""
+def masked_mse(pred, ref, mask, reduction="mean"):
+    """quantizer.py:142-156 -- MSELoss('mean') over ALL elements; masked tokens contribute zeros.  reduction="sum" is what
+    the loop switches to under gradient accumulation (quantizer.py:436-439)."""
     if mask is not None:
-        return F.mse_loss((pred * mask).to(torch.float32), (ref * mask).to(torch.float32))
-    return F.mse_loss(pred.to(torch.float32), ref.to(torch.float32))
+        return F.mse_loss((pred * mask).to(torch.float32), (ref * mask).to(torch.float32), reduction=reduction)
+    return F.mse_loss(pred.to(torch.float32), ref.to(torch.float32), reduction=reduction)
 
 
 @dataclass
@@ -274,8 +275,11 @@ class BlockTuner:
 
     def __init__(self, block, inputs, others, fp_outputs, scheme_of, iters=200, batch_size=8, lr=None, minmax_lr=None,
                  token_masks=None, enable_minmax_tuning=True, nv_global_scales=None, amp=True, not_use_best_mse=False,
-                 sampler=None, alg_ext=False, imatrices=None, outlier_loss=None):
+                 sampler=None, alg_ext=False, imatrices=None, outlier_loss=None, gradient_accumulate_steps=1):
         self.block, self.inputs, self.others, self.fp_outputs = block, inputs, others, fp_outputs
+        # gradient accumulation (quantizer.py:436-452, 480-500): an iteration = batch_size * steps samples run as micro-batches
+        # of batch_size with MSELoss(reduction="sum"); without a token mask num_elm is fixed before the loop
+        self.accum, self.micro_bs, self.micro_losses = int(gradient_accumulate_steps), batch_size, []
         self.iters, self.token_masks, self.amp, self.alg_ext = iters, token_masks, amp, alg_ext
         self.not_use_best_mse = not_use_best_mse
         nsamples = len(inputs)
@@ -304,33 +308,40 @@ class BlockTuner:
             for tl in wrapped.values():
                 tl.min_scale.requires_grad_(False)
                 tl.max_scale.requires_grad_(False)
-        gbs = min(nsamples, batch_size)
+        gbs = min(nsamples, batch_size * self.accum)
+        self.fixed_num_elm = 1
+        if self.accum != 1 and not token_masks:
+            self.fixed_num_elm = sum(int(inputs[i].numel()) for i in range(gbs))
         self.sampler = sampler if sampler is not None else IndexSampler(nsamples, gbs)
         self.best_loss = torch.finfo(torch.float).max
 
     def step(self, it):
         res, wrapped, token_masks = self.res, self.wrapped, self.token_masks
-        idx = self.sampler.next_batch()
-        res.batches.append(list(idx))
-        num_elm = 1
-        mask = None
+        gidx = self.sampler.next_batch()
+        res.batches.append(list(gidx))
+        num_elm = self.fixed_num_elm
         if token_masks:
-            num_elm = sum(int(torch.count_nonzero(token_masks[i]).item()) for i in idx)
-            mask = torch.cat([token_masks[i] for i in idx], dim=0).unsqueeze(-1)
-        ref = torch.cat([self.fp_outputs[i] for i in idx], dim=0)
-        x, sel = select_batch(self.inputs, self.others, idx)
-        pred = block_forward(self.block, x, sel, self.amp)
-        if self.outlier_loss:
-            loss = outlier_suppressed_loss(pred, ref, mask)
-        elif self.alg_ext:
-            # SignRoundV2Quantizer._get_loss falls back to super()._get_loss WITHOUT forwarding valid_token_mask
-            # (sign_roundv2/quantizer.py:399): plain MSE over every token; num_elm below still counts valid tokens only
-            loss = masked_mse(pred, ref, None)
-        else:
-            loss = masked_mse(pred, ref, mask)
-        num_elm = 1 if num_elm <= 0 else num_elm
-        total = loss.item() / num_elm
-        (loss * 1000).backward()
+            num_elm = sum(int(torch.count_nonzero(token_masks[i]).item()) for i in gidx)
+        reduction = "sum" if self.accum != 1 else "mean"
+        total = 0.0
+        for start in range(0, len(gidx), self.micro_bs):
+            idx = gidx[start:start + self.micro_bs]
+            mask = torch.cat([token_masks[i] for i in idx], dim=0).unsqueeze(-1) if token_masks else None
+            ref = torch.cat([self.fp_outputs[i] for i in idx], dim=0)
+            x, sel = select_batch(self.inputs, self.others, idx)
+            pred = block_forward(self.block, x, sel, self.amp)
+            if self.outlier_loss:
+                loss = outlier_suppressed_loss(pred, ref, mask)
+            elif self.alg_ext:
+                # SignRoundV2Quantizer._get_loss falls back to super()._get_loss WITHOUT forwarding valid_token_mask
+                # (sign_roundv2/quantizer.py:399): plain MSE over every token; num_elm still counts valid tokens only
+                loss = masked_mse(pred, ref, None, reduction)
+            else:
+                loss = masked_mse(pred, ref, mask, reduction)
+            num_elm = 1 if num_elm <= 0 else num_elm
+            total += loss.item() / num_elm
+            self.micro_losses.append(float(loss.item()))
+            (loss * 1000).backward()
         res.losses.append(total)
         if total < self.best_loss:
             self.best_loss = total
@@ -363,16 +374,20 @@ class BlockTuner:
 
 def tune_block(block, inputs, others, fp_outputs, scheme_of, iters=200, batch_size=8, lr=None, minmax_lr=None,
                token_masks=None, enable_minmax_tuning=True, nv_global_scales=None, amp=True,
-               not_use_best_mse=False, sampler=None, alg_ext=False, imatrices=None, outlier_loss=None) -> TuneResult:
+               not_use_best_mse=False, sampler=None, alg_ext=False, imatrices=None, outlier_loss=None,
+               gradient_accumulate_steps=1) -> TuneResult:
     """quantize_block: `inputs`/`fp_outputs` are per-sample lists of [1,S,H]; `token_masks` per-sample [1,S]
     long tensors (1 = valid) or None.  Mutates `block` in place (qdq weights + scale/zp attributes)."""
     tuner = BlockTuner(block, inputs, others, fp_outputs, scheme_of, iters, batch_size, lr, minmax_lr, token_masks,
-                       enable_minmax_tuning, nv_global_scales, amp, not_use_best_mse, sampler, alg_ext, imatrices, outlier_loss)
+                       enable_minmax_tuning, nv_global_scales, amp, not_use_best_mse, sampler, alg_ext, imatrices, outlier_loss,
+                       gradient_accumulate_steps)
     if not tuner.wrapped:
         return tuner.res
     for it in range(iters):
         tuner.step(it)
-    return tuner.finish()
+    res = tuner.finish()
+    res.micro_losses = tuner.micro_losses
+    return res
 
 
 # --------------------------------------------------------------------------------------------

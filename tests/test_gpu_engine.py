@@ -247,3 +247,65 @@ def test_eager_attention_block_keeps_cached_mask(golden_dir):
     q.quantize_block(blk, [t.to(DEV) for t in b["inputs"]], others, [t.to(DEV) for t in refs], None, None,
                      input_ids=b["input_ids"], sampler=S.ReplaySampler(batches))
     assert q.last_result.losses[0] == pytest.approx(ores.losses[0], rel=3e-2)
+
+
+def test_gradient_accumulation_vs_oracle(golden_dir):
+    """gradient_accumulate_steps = 2 (quantizer.py:436-452): iterations of 2 micro-batches x 2 samples, sum-reduced loss, one
+    sign-SGD step per iteration.  The oracle's accumulation is pinned bit-exact against the live reference
+    (oracle/diff_fuzz.py --loops, case accum2_bs2)."""
+    rec = _load(golden_dir, "w4a16_sym_g32")
+    b = rec["blocks"][0]
+    osc = S.LayerScheme(4, 32, True, "int")
+    masks = [(ids != -100).to(torch.long) for ids in b["input_ids"]]
+    iters = 30
+    random.seed(77)
+    oblk = _tiny_block(b["block_state"])
+    ores = S.tune_block(oblk, b["inputs"], b["others"], b["fp_outputs"], lambda n, m: osc, iters=iters, batch_size=2,
+                        token_masks=masks, gradient_accumulate_steps=2)
+    o_mse = _block_mse(oblk, b["inputs"], b["others"], b["fp_outputs"], masks, "cpu")
+    blk = _tiny_block(b["block_state"], DEV)
+    for p in blk.parameters():
+        p.requires_grad_(False)
+    q = SignRoundQuantizer(parse_scheme("W4A16", {"group_size": 32}), iters=iters, batch_size=2, gradient_accumulate_steps=2)
+    q.quantize_block(blk, [t.to(DEV) for t in b["inputs"]], b["others"], [t.to(DEV) for t in b["fp_outputs"]], None, None,
+                     input_ids=b["input_ids"], sampler=S.ReplaySampler(ores.batches))
+    res = q.last_result
+    assert res.batches == ores.batches and len(res.batches[0]) == 4
+    assert res.losses[0] == pytest.approx(ores.losses[0], rel=2e-2)
+    assert res.best_loss <= res.losses[0] + 1e-12
+    g_mse = _block_mse(blk, b["inputs"], b["others"], b["fp_outputs"], masks, DEV)
+    assert g_mse == pytest.approx(o_mse, rel=0.25), (g_mse, o_mse)
+
+
+@pytest.mark.parametrize("opts", [dict(enable_minmax_tuning=False), dict(not_use_best_mse=True), dict(lr=0.01, minmax_lr=0.02)])
+def test_loop_options_vs_oracle(golden_dir, opts):
+    """The loop options the oracle is pinned on against the live reference (oracle/diff_fuzz.py --loops) on the GPU engine."""
+    rec = _load(golden_dir, "w4a16_sym_g32")
+    b = rec["blocks"][0]
+    osc = S.LayerScheme(4, 32, True, "int")
+    masks = [(ids != -100).to(torch.long) for ids in b["input_ids"]]
+    iters = 30
+    random.seed(99)
+    oblk = _tiny_block(b["block_state"])
+    ores = S.tune_block(oblk, b["inputs"], b["others"], b["fp_outputs"], lambda n, m: osc, iters=iters, batch_size=4,
+                        token_masks=masks, **opts)
+    o_mse = _block_mse(oblk, b["inputs"], b["others"], b["fp_outputs"], masks, "cpu")
+    blk = _tiny_block(b["block_state"], DEV)
+    for p in blk.parameters():
+        p.requires_grad_(False)
+    q = SignRoundQuantizer(parse_scheme("W4A16", {"group_size": 32}), iters=iters, batch_size=4, **opts)
+    q.quantize_block(blk, [t.to(DEV) for t in b["inputs"]], b["others"], [t.to(DEV) for t in b["fp_outputs"]], None, None,
+                     input_ids=b["input_ids"], sampler=S.ReplaySampler(ores.batches))
+    res = q.last_result
+    assert res.losses[0] == pytest.approx(ores.losses[0], rel=2e-2)
+    if opts.get("not_use_best_mse"):
+        assert res.best_iter == iters - 1
+    if opts.get("enable_minmax_tuning") is False:                       # scales must still be the RTN ones
+        for name, lay in b["layers"].items():
+            mod = blk.get_submodule(name)
+            sc0 = ops.qdq_fwd(ops.make_spec("int_sym", 4, 32, *mod.weight.shape), torch.load(
+                os.path.join(golden_dir, "block_w4a16_sym_g32.pt"), weights_only=False)["blocks"][0]["block_state"][name + ".weight"].to(DEV),
+                want_wq=False, want_scale=True)[1]
+            assert torch.equal(mod.scale.reshape(-1).cpu(), sc0.cpu().reshape(-1)), name
+    g_mse = _block_mse(blk, b["inputs"], b["others"], b["fp_outputs"], masks, DEV)
+    assert g_mse == pytest.approx(o_mse, rel=0.25), (g_mse, o_mse)

@@ -144,8 +144,12 @@ def test_fused_update_flag_off_and_has_grad():
     assert not torch.equal(d["v"].cpu().reshape(v.shape), v)                             # but the step happened
     d = _device_state(spec, w, v, mn, mx, init, gs, gq)
     _run(spec, d, lr_tab, torch.ones(1, dtype=torch.int32, device=DEV), hi, has_grad=torch.zeros(1, dtype=torch.int32, device=DEV))
-    assert torch.equal(d["v"].cpu().reshape(v.shape), v) and torch.equal(d["mx"].cpu(), mx)   # layer without a gradient:
-    assert float(d["wq"].abs().max()) == 0.0 and float(d["best_v"].min()) == -7.0             # untouched
+    assert torch.equal(d["v"].cpu().reshape(v.shape), v) and torch.equal(d["mx"].cpu(), mx)   # layer without a gradient: not
+    assert float(d["wq"].abs().max()) == 0.0                                                  # stepped, no new Wq ...
+    assert torch.equal(d["best_v"].cpu().reshape(v.shape), v) and torch.equal(d["best_mx"].cpu(), mx)   # ... but snapshotted
+    d = _device_state(spec, w, v, mn, mx, init, gs, gq)
+    _run(spec, d, lr_tab, torch.zeros(1, dtype=torch.int32, device=DEV), hi, has_grad=torch.zeros(1, dtype=torch.int32, device=DEV))
+    assert float(d["best_v"].min()) == -7.0 and torch.equal(d["v"].cpu().reshape(v.shape), v)  # no flag: nothing at all
 
 
 @pytest.mark.parametrize("name,qname,bits,g,n,k,with_init", [CASES[0], CASES[4], CASES[7]])
