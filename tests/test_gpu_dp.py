@@ -166,7 +166,9 @@ def _check(tag, backend, tmp_path, world=2):
     if not alg_ext and v1_one is not None:
         agree = float((r0["v1"] == v1_one).float().mean())
         assert agree >= 0.99, agree
-    assert r0["mse"] == pytest.approx(one["mse"], rel=0.25), (r0["mse"], one["mse"])
+    # MoE: top-2 routing is discontinuous -- the sharded attention layers move a few tokens to other experts, so the two
+    # trajectories differ more than for a dense block (tests/test_gpu_moe.py explains the 7 % a single token makes)
+    assert r0["mse"] == pytest.approx(one["mse"], rel=0.4 if "mixtral" in tag else 0.25), (r0["mse"], one["mse"])
     assert min(r0["losses"]) <= r0["losses"][0]
 
 

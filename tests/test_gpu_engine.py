@@ -217,8 +217,8 @@ def test_autoround_model_level(golden_dir, tag, tmp_path):
 
 def test_eager_attention_block_keeps_cached_mask(golden_dir):
     """with attn_implementation='eager' HF applies NO mask when attention_mask is None, so the engine must keep
-    the cached mask there.  A bool causal mask (what transformers >= 5 caches) on an eager block must give the loss the
-    oracle gets with the same mask through sdpa -- bidirectional attention would be off by orders of magnitude."""
+    the cached mask there.  The additive causal mask HF prepares for eager attention (0 / dtype-min) on an eager block must
+    give the loss the oracle gets with the same mask through sdpa -- bidirectional attention is off by orders of magnitude."""
     from transformers.models.llama.modeling_llama import LlamaDecoderLayer
 
     rec = _load(golden_dir, "w4a16_sym_g32")
@@ -227,8 +227,9 @@ def test_eager_attention_block_keeps_cached_mask(golden_dir):
     masks = [(ids != -100).to(torch.long) for ids in b["input_ids"]]
     seq = b["inputs"][0].shape[1]
     causal = torch.ones(seq, seq, dtype=torch.bool).tril().reshape(1, 1, seq, seq)
+    additive = torch.zeros(1, 1, seq, seq, dtype=torch.bfloat16).masked_fill(~causal, torch.finfo(torch.bfloat16).min)
     others = dict(b["others"])
-    others["attention_mask"] = [causal.clone() for _ in b["inputs"]]
+    others["attention_mask"] = [additive.clone() for _ in b["inputs"]]
     iters = 6
     oblk = _tiny_block(b["block_state"])
     with torch.no_grad():
