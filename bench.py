@@ -276,6 +276,12 @@ def run_ours(args):
     e2e_ms, comp_ms = t.tolist()
 
     dp_probe = collective_probe(dev, world, cfg) if world > 1 else None
+    dp_timeline = None
+    if world > 1 and "mixtral" not in cfg["model"]:
+        try:                                   # every rank runs the extra block (collectives inside); rank 0 reports it
+            dp_timeline = iteration_timeline(dev, peaks(), cfg, args.config, dp=ar.dp)
+        except Exception as e:  # noqa: BLE001
+            dp_timeline = {"error": repr(e)[:200]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -313,6 +319,8 @@ def run_ours(args):
     }
     if dp_probe is not None:
         line["dp_probe"] = dp_probe
+    if dp_timeline is not None:
+        line["dp_iteration_timeline"] = dp_timeline
     if world == 1:
         roof = gemm_roofline(dev, pk, cfg)
         if "mixtral" in cfg["model"]:
@@ -431,7 +439,7 @@ def gemm_roofline(dev, pk, cfg):
             "how": "%d GEMM launches of one iteration replayed x10 after 3 warm-ups; operands 3.4 GB >> L2" % nlaunch}
 
 
-def iteration_timeline(dev, pk, cfg, cfg_name):
+def iteration_timeline(dev, pk, cfg, cfg_name, dp=None):
     """Kernel timeline of ONE steady-state iteration inside the CUDA-graph replay of a real block (CUPTI through
     torch.profiler; 14 iterations, the 6th is read): where the iteration's time goes and what the GEMMs achieve IN CONTEXT
     (back to back with everything else, at the sustained clock).  A diagnostic taken under the profiler -- never a value."""
@@ -457,7 +465,7 @@ def iteration_timeline(dev, pk, cfg, cfg_name):
     sk = dict(cfg["scheme"])
     alg_ext = bool(sk.pop("enable_alg_ext", False))
     scheme = parse_scheme(sk.pop("scheme"), sk)
-    q = SignRoundQuantizer(scheme, iters=14, batch_size=BATCH, enable_alg_ext=alg_ext)
+    q = SignRoundQuantizer(scheme, iters=14, batch_size=BATCH, enable_alg_ext=alg_ext, dp=dp)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         q.quantize_block(blk, xs, others, refs, None, None, input_ids=None)
@@ -472,14 +480,29 @@ def iteration_timeline(dev, pk, cfg, cfg_name):
     agg = {}
     for e in it:
         name = e.name
-        key = ("ar::gemm_kernel" if "gemm_kernel" in name else "cudnn sdpa" if ("sdpa" in name or "cudnn" in name or "fmha" in name)
+        key = ("nccl" if "nccl" in name.lower() else
+               "ar::gemm_kernel" if "gemm_kernel" in name else "cudnn sdpa" if ("sdpa" in name or "cudnn" in name or "fmha" in name)
                else "ar::fq_update_kernel" if "fq_update" in name else "ar::swiglu" if "swiglu" in name
                else "aten elementwise" if "at::native" in name else "ar:: other" if name.startswith(("ar::", "void ar::")) else "other")
         c, t_ = agg.get(key, (0, 0.0))
         agg[key] = (c + 1, t_ + (e.time_range.end - e.time_range.start) / 1e3)
-    flops_iter = (BATCH * SEQLEN) * (6 * sum(n * k for _, n, k, _ in cfg["linears"]) - 2 * sum(n * k for _, n, k, dx in cfg["linears"] if not dx))
+    world = dp.world if dp is not None else 1
+    flops_iter = (BATCH * SEQLEN) * (6 * sum(n * k for _, n, k, _ in cfg["linears"]) - 2 * sum(n * k for _, n, k, dx in cfg["linears"] if not dx)) / world
     gemm_ms = agg.get("ar::gemm_kernel", (0, 0.0))[1]
+    # time covered by at least one non-NCCL kernel (streams overlap under data parallelism): what is left is exposed communication / idle
+    ivs = sorted((e.time_range.start, e.time_range.end) for e in it if "nccl" not in e.name.lower())
+    covered, cur_s, cur_e = 0.0, None, None
+    for a, b in ivs:
+        if cur_e is None or a > cur_e:
+            if cur_e is not None:
+                covered += cur_e - cur_s
+            cur_s, cur_e = a, b
+        else:
+            cur_e = max(cur_e, b)
+    if cur_e is not None:
+        covered += cur_e - cur_s
     return {"iteration_ms": round(span, 3), "kernels": len(it), "gemm_ms": round(gemm_ms, 3),
+            "compute_covered_ms": round(covered / 1e3, 3), "not_covered_by_compute_ms": round(span - covered / 1e3, 3),
             "gemm_tflops_in_context": round(flops_iter / (gemm_ms / 1e3) / 1e12, 1) if gemm_ms else None,
             "frac_of_sustained_peak": round(flops_iter / (gemm_ms / 1e3) / 1e12 / pk["sustained"], 4) if gemm_ms else None,
             "by_kernel_ms": {k: [c, round(t_, 3)] for k, (c, t_) in sorted(agg.items(), key=lambda kv: -kv[1][1])},

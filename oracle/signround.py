@@ -120,9 +120,10 @@ class TunableLinear(nn.Module):
     def bake(self, best):
         """unwrapper: qdq with the best params -> weight.data; attach scale / zp / weight_global_scale."""
         best = best or {}
-        v = best.get("value", torch.tensor(0.0))
-        mn = best.get("min_scale", torch.tensor(1.0))
-        mx = best.get("max_scale", torch.tensor(1.0))
+        dev = self.linear.weight.device
+        v = best.get("value", torch.tensor(0.0, device=dev))
+        mn = best.get("min_scale", torch.tensor(1.0, device=dev))
+        mx = best.get("max_scale", torch.tensor(1.0, device=dev))
         wq, scale, zp = self.qdq(v, mn, mx)
         lin = self.linear
         lin.weight.data.copy_(wq)
