@@ -239,8 +239,9 @@ static int check_spec(const ar_qspec* q) {
   AR_REQUIRE(q != nullptr, AR_E_BADARG, "qspec is null");
   AR_REQUIRE(q->n > 0 && q->k > 0, AR_E_BADARG, "bad shape n=%d k=%d", q->n, q->k);
   const int g = q->group_size;
-  AR_REQUIRE(g == 16 || g == 32 || g == 64 || g == 128 || g == 256, AR_E_UNSUPPORTED,
-             "group_size %d not supported (16/32/64/128/256)", g);
+  const bool is_int_t = (q->dtype == AR_DT_INT_SYM || q->dtype == AR_DT_INT_ASYM);
+  AR_REQUIRE(g == 16 || g == 32 || g == 64 || g == 128 || g == 256 || (is_int_t && g == q->k && q->k % 8 == 0), AR_E_UNSUPPORTED,
+             "group_size %d not supported (16/32/64/128/256, or == K (per-row groups, int types, K %% 8 == 0))", g);
   if (q->dtype == AR_DT_INT_SYM || q->dtype == AR_DT_INT_ASYM)
     AR_REQUIRE(q->bits == 2 || q->bits == 3 || q->bits == 4 || q->bits == 8, AR_E_UNSUPPORTED, "int bits %d", q->bits);
   else if (q->dtype == AR_DT_MX_FP4 || q->dtype == AR_DT_NV_FP4)
@@ -248,6 +249,11 @@ static int check_spec(const ar_qspec* q) {
   else
     AR_REQUIRE(false, AR_E_BADARG, "unknown dtype %d", q->dtype);
   return AR_OK;
+}
+
+static bool row_mode(const ar_qspec* q) {
+  const int g = q->group_size;
+  return !(g == 16 || g == 32 || g == 64 || g == 128 || g == 256);
 }
 
 static QArgs make_args(const ar_qspec* q, const void* w, const float* v, const float* mn, const float* mx,
@@ -425,6 +431,163 @@ static void launch_upd_g(int g, dim3 grid, cudaStream_t st, const QArgs& a, cons
   }
 }
 
+// ------------------------------------------------------------------------------------------ per-row groups
+// group_size = -1 (per output channel) or K < group_size: the reference keeps the weight as [N, K] and every ROW is one
+// group (reshape_pad_tensor_by_group_size, data_type/utils.py:57-61).  One warp per row, lanes stride over 8-element chunks;
+// int types only (the fp4 formats fix their group size).  K % 8 == 0.
+constexpr int kRowWarps = kThreads / 32;
+
+template <class Ctx>
+__device__ __forceinline__ void row_group_in(const QArgs& a, int row, int lane, GroupIn& gi, Ctx& ctx) {
+  gi.thr = a.thr;
+  gi.plain = (a.mn == nullptr) && (a.mx == nullptr);
+  gi.gscale = 0.f;
+  gi.mn = a.mn ? a.mn[row] : 1.f;
+  gi.mx = a.mx ? a.mx[row] : 1.f;
+  gi.has_init = (a.init != nullptr);
+  gi.init = a.init ? a.init[row] : 1.f;
+  ctx.init(a.bits);
+  if (a.wmin != nullptr) {
+    gi.wmin = bf16_bits_to_f32(a.wmin[row]);
+    gi.wmax = bf16_bits_to_f32(a.wmax[row]);
+  } else {
+    float lo = 0.f, hi = 0.f;
+    for (int c = lane; c < a.k / 8; c += 32) {
+      float w[8];
+      load_w8(a.w, (int64_t)row * a.k, c * 8, a.k, true, w);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { lo = fminf(lo, w[i]); hi = fmaxf(hi, w[i]); }
+    }
+    gi.wmin = group_min<32>(lo);
+    gi.wmax = group_max<32>(hi);
+  }
+  ctx.setup(gi);
+}
+
+__global__ void __launch_bounds__(kThreads) group_minmax_row_kernel(QArgs a, uint16_t* omin, uint16_t* omax) {
+  const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= a.n) return;
+  float lo = 0.f, hi = 0.f;
+  for (int c = lane; c < a.k / 8; c += 32) {
+    float w[8];
+    load_w8(a.w, (int64_t)row * a.k, c * 8, a.k, true, w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { lo = fminf(lo, w[i]); hi = fmaxf(hi, w[i]); }
+  }
+  lo = group_min<32>(lo);
+  hi = group_max<32>(hi);
+  if (lane == 0) { omin[row] = f32_to_bf16_bits(lo); omax[row] = f32_to_bf16_bits(hi); }
+}
+
+template <class Ctx>
+__global__ void __launch_bounds__(kThreads) qdq_fwd_row_kernel(QArgs a, uint16_t* wq, __half* scale_out, float* zp_out) {
+  const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= a.n) return;
+  Ctx ctx;
+  GroupIn gi;
+  row_group_in<Ctx>(a, row, lane, gi, ctx);
+  if (wq != nullptr) {
+    for (int c = lane; c < a.k / 8; c += 32) {
+      float w[8], v[8];
+      load_w8(a.w, (int64_t)row * a.k, c * 8, a.k, true, w);
+      if (a.v) load_f8(a.v, (int64_t)row * a.k + c * 8, v);
+      uint32_t packed[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t lo = f32_to_bf16_bits(ctx.fwd(w[2 * i], a.v ? v[2 * i] : 0.f));
+        const uint32_t hi = f32_to_bf16_bits(ctx.fwd(w[2 * i + 1], a.v ? v[2 * i + 1] : 0.f));
+        packed[i] = lo | (hi << 16);
+      }
+      *reinterpret_cast<U4*>(wq + (int64_t)row * a.k + c * 8) = U4{packed[0], packed[1], packed[2], packed[3]};
+    }
+  }
+  if (lane == 0) {
+    if (scale_out) scale_out[row] = __float2half_rn(ctx.scale_out());
+    if (zp_out) zp_out[row] = ctx.zp_out();
+  }
+}
+
+template <class Ctx>
+__global__ void __launch_bounds__(kThreads) fq_update_row_kernel(QArgs a, UpdArgs u) {
+  const int row = u.row0 + blockIdx.x * kRowWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= u.row1) return;
+  const bool no_grad = (u.has_grad != nullptr) && (*u.has_grad == 0);
+  const bool snap = (u.flag != nullptr) && (*u.flag != 0) && (u.best_v != nullptr);
+  if (no_grad && !snap) return;
+  const int iter = u.it_ptr ? *u.it_ptr : u.iter;
+  const float lr_v = u.lr_table[2 * iter], lr_s = u.lr_table[2 * iter + 1];
+  a.v = u.v; a.mn = u.mn; a.mx = u.mx;
+  Ctx ctx;
+  GroupIn gi;
+  row_group_in<Ctx>(a, row, lane, gi, ctx);
+  const int64_t wrow = (int64_t)row * a.k, grow = (int64_t)(row - u.gq_row0) * a.k;
+  if (no_grad) {                                     // snapshot only (see fq_update_kernel)
+    for (int c = lane; c < a.k / 8; c += 32) {
+      *reinterpret_cast<float4*>(u.best_v + wrow + c * 8) = *reinterpret_cast<const float4*>(u.v + wrow + c * 8);
+      *reinterpret_cast<float4*>(u.best_v + wrow + c * 8 + 4) = *reinterpret_cast<const float4*>(u.v + wrow + c * 8 + 4);
+    }
+    if (lane == 0) { if (u.best_mx) u.best_mx[row] = gi.mx; if (u.best_mn && u.mn) u.best_mn[row] = gi.mn; }
+    return;
+  }
+  // pass 1: the group sums of the scale gradients
+  GroupAcc acc;
+  for (int c = lane; c < a.k / 8; c += 32) {
+    float w[8], v[8], g[8], d;
+    load_w8(a.w, wrow, c * 8, a.k, true, w);
+    load_w8(u.gq, grow, c * 8, a.k, true, g);
+    load_f8(u.v, wrow + c * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ctx.bwd(w[i], v[i], g[i], d, acc);
+  }
+  acc.a = group_sum<32>(acc.a);
+  acc.b = group_sum<32>(acc.b);
+  float gmn, gmx;
+  ctx.finish(acc, gi, gmn, gmx);
+  const float old_mn = gi.mn, old_mx = gi.mx;
+  Ctx next = ctx;
+  GroupIn gn = gi;
+  gn.mx = clampf(sign_step(gi.mx, lr_s, gmx), 0.f, u.clamp_hi);
+  if (u.mn) gn.mn = clampf(sign_step(gi.mn, lr_s, gmn), 0.f, u.clamp_hi);
+  next.setup(gn);
+  // pass 2: dV again (same parameters), snapshot, step, next iteration's fake-quant weight
+  for (int c = lane; c < a.k / 8; c += 32) {
+    float w[8], v[8], g[8], d[8];
+    GroupAcc dummy;
+    load_w8(a.w, wrow, c * 8, a.k, true, w);
+    load_w8(u.gq, grow, c * 8, a.k, true, g);
+    load_f8(u.v, wrow + c * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ctx.bwd(w[i], v[i], g[i], d[i], dummy);
+    if (u.dv_dbg) {
+      *reinterpret_cast<float4*>(u.dv_dbg + wrow + c * 8) = make_float4(d[0], d[1], d[2], d[3]);
+      *reinterpret_cast<float4*>(u.dv_dbg + wrow + c * 8 + 4) = make_float4(d[4], d[5], d[6], d[7]);
+    }
+    if (snap) {
+      *reinterpret_cast<float4*>(u.best_v + wrow + c * 8) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(u.best_v + wrow + c * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = sign_step(v[i], lr_v, d[i]);
+    *reinterpret_cast<float4*>(u.v + wrow + c * 8) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(u.v + wrow + c * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    uint32_t packed[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t lo = f32_to_bf16_bits(next.fwd(w[2 * i], v[2 * i]));
+      const uint32_t hi = f32_to_bf16_bits(next.fwd(w[2 * i + 1], v[2 * i + 1]));
+      packed[i] = lo | (hi << 16);
+    }
+    *reinterpret_cast<U4*>(u.wq + wrow + c * 8) = U4{packed[0], packed[1], packed[2], packed[3]};
+  }
+  if (lane == 0) {
+    if (u.dmx_dbg) u.dmx_dbg[row] = gmx;
+    if (u.dmn_dbg) u.dmn_dbg[row] = gmn;
+    if (snap) { if (u.best_mx) u.best_mx[row] = old_mx; if (u.best_mn && u.mn) u.best_mn[row] = old_mn; }
+    u.mx[row] = gn.mx;
+    if (u.mn) u.mn[row] = gn.mn;
+  }
+}
+
 }  // namespace ar
 
 using namespace ar;
@@ -437,9 +600,16 @@ extern "C" int ar_qdq_fwd(const ar_qspec* q, const void* w, const float* v, cons
   AR_REQUIRE((wmin == nullptr) == (wmax == nullptr), AR_E_BADARG, "wmin/wmax must both be given or both null");
   AR_REQUIRE(q->dtype != AR_DT_NV_FP4 || gscale != nullptr, AR_E_BADARG, "nv_fp4 needs gscale");
   const QArgs a = make_args(q, w, v, mn, mx, wmin, wmax, gscale);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (row_mode(q)) {
+    const dim3 rgrid((unsigned)((a.n + kRowWarps - 1) / kRowWarps));
+    if (q->dtype == AR_DT_INT_SYM) qdq_fwd_row_kernel<IntSym><<<rgrid, kThreads, 0, st>>>(a, (uint16_t*)wq, (__half*)scale_out, nullptr);
+    else qdq_fwd_row_kernel<IntAsym><<<rgrid, kThreads, 0, st>>>(a, (uint16_t*)wq, (__half*)scale_out, zp_out);
+    AR_CHECK_LAUNCH();
+    return AR_OK;
+  }
   const int64_t chunks = (int64_t)a.n * (a.kpad / 8);
   const dim3 grid((unsigned)((chunks + kThreads - 1) / kThreads));
-  cudaStream_t st = (cudaStream_t)stream;
   const int g = q->group_size;
   if (q->dtype == AR_DT_INT_SYM) {
     launch_fwd_g<IntSym, false, SCALE_F16>(g, grid, st, a, (uint16_t*)wq, scale_out, nullptr);
@@ -459,6 +629,7 @@ extern "C" int ar_qdq_bwd(const ar_qspec* q, const void* w, const float* v, cons
                           float* dmin, float* dmax, int accumulate, void* stream) {
   if (int rc = check_spec(q)) return rc;
   AR_REQUIRE(w && gq && dv, AR_E_BADARG, "w/gq/dv must be non-null");
+  AR_REQUIRE(!row_mode(q), AR_E_UNSUPPORTED, "ar_qdq_bwd: per-row groups are served by ar_fq_update only");
   AR_REQUIRE((wmin == nullptr) == (wmax == nullptr), AR_E_BADARG, "wmin/wmax must both be given or both null");
   AR_REQUIRE(q->dtype != AR_DT_NV_FP4 || gscale != nullptr, AR_E_BADARG, "nv_fp4 needs gscale");
   const QArgs a = make_args(q, w, v, mn, mx, wmin, wmax, gscale);
@@ -483,9 +654,14 @@ extern "C" int ar_group_minmax(const ar_qspec* q, const void* w, void* wmin, voi
   if (int rc = check_spec(q)) return rc;
   AR_REQUIRE(w && wmin && wmax, AR_E_BADARG, "null pointer");
   const QArgs a = make_args(q, w, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (row_mode(q)) {
+    group_minmax_row_kernel<<<(unsigned)((a.n + kRowWarps - 1) / kRowWarps), kThreads, 0, st>>>(a, (uint16_t*)wmin, (uint16_t*)wmax);
+    AR_CHECK_LAUNCH();
+    return AR_OK;
+  }
   const int64_t chunks = (int64_t)a.n * (a.kpad / 8);
   const dim3 grid((unsigned)((chunks + kThreads - 1) / kThreads));
-  cudaStream_t st = (cudaStream_t)stream;
   switch (q->group_size) {
     case 16: group_minmax_kernel<16><<<grid, kThreads, 0, st>>>(a, (uint16_t*)wmin, (uint16_t*)wmax); break;
     case 32: group_minmax_kernel<32><<<grid, kThreads, 0, st>>>(a, (uint16_t*)wmin, (uint16_t*)wmax); break;
@@ -530,9 +706,16 @@ extern "C" int ar_fq_update(const ar_qspec* q, const void* w, float* v, float* m
   u.v = v; u.mn = mn; u.mx = mx; u.best_v = best_v; u.best_mn = best_mn; u.best_mx = best_mx; u.flag = flag;
   u.lr_table = lr_table; u.iter = iter; u.it_ptr = it_ptr; u.clamp_hi = clamp_hi; u.wq = (uint16_t*)wq_out;
   u.dv_dbg = dv_dbg; u.dmn_dbg = dmn_dbg; u.dmx_dbg = dmx_dbg; u.has_grad = has_grad;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (row_mode(q)) {
+    const dim3 rgrid((unsigned)((row1 - row0 + kRowWarps - 1) / kRowWarps));
+    if (q->dtype == AR_DT_INT_SYM) fq_update_row_kernel<IntSym><<<rgrid, kThreads, 0, st>>>(a, u);
+    else fq_update_row_kernel<IntAsym><<<rgrid, kThreads, 0, st>>>(a, u);
+    AR_CHECK_LAUNCH();
+    return AR_OK;
+  }
   const int64_t chunks = (int64_t)(row1 - row0) * (a.kpad / 8);
   const dim3 grid((unsigned)((chunks + kThreads - 1) / kThreads));
-  cudaStream_t st = (cudaStream_t)stream;
   const int g = q->group_size;
   if (q->dtype == AR_DT_INT_SYM) launch_upd_g<IntSym, false>(g, grid, st, a, u);
   else if (q->dtype == AR_DT_INT_ASYM) launch_upd_g<IntAsym, false>(g, grid, st, a, u);

@@ -59,6 +59,16 @@ class Spec:
 
 def make_spec(name: str, bits: int, group_size: int, n: int, k: int, q_scale_thresh: float = 1e-5,
               scale_bound_hi: float = 1.0) -> Spec:
+    """group_size -1, or a weight narrower than the group (K < group_size), means one group per ROW in the reference
+    (reshape_pad_tensor_by_group_size, data_type/utils.py:57-61): encoded as group_size == K (int types only)."""
+    if group_size == 0:
+        raise NotImplementedError("group_size = 0 (one group per tensor) is outside the B200 hot path")
+    if group_size == -1 or k < group_size:
+        if name not in ("int_sym", "int_asym"):
+            raise NotImplementedError(f"{name}: per-row groups (group_size=-1 / K < group_size) exist for the int types only")
+        if k % 8:
+            raise NotImplementedError("per-row groups need K % 8 == 0")
+        group_size = k
     return Spec(DTYPE_IDS[name], bits, group_size, n, k, q_scale_thresh, scale_bound_hi)
 
 

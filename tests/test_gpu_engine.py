@@ -310,3 +310,36 @@ def test_loop_options_vs_oracle(golden_dir, opts):
             assert torch.equal(mod.scale.reshape(-1).cpu(), sc0.cpu().reshape(-1)), name
     g_mse = _block_mse(blk, b["inputs"], b["others"], b["fp_outputs"], masks, DEV)
     assert g_mse == pytest.approx(o_mse, rel=0.25), (g_mse, o_mse)
+
+
+def test_per_channel_block_vs_oracle(golden_dir):
+    """group_size = -1 (one group per output channel) through the whole loop: per-row update kernels, pack with g = K."""
+    rec = _load(golden_dir, "w4a16_sym_g32")
+    b = rec["blocks"][0]
+    osc = S.LayerScheme(4, -1, True, "int")
+    masks = [(ids != -100).to(torch.long) for ids in b["input_ids"]]
+    iters = 30
+    random.seed(5)
+    oblk = _tiny_block(b["block_state"])
+    ores = S.tune_block(oblk, b["inputs"], b["others"], b["fp_outputs"], lambda n, m: osc, iters=iters, batch_size=4, token_masks=masks)
+    o_mse = _block_mse(oblk, b["inputs"], b["others"], b["fp_outputs"], masks, "cpu")
+    blk = _tiny_block(b["block_state"], DEV)
+    for p in blk.parameters():
+        p.requires_grad_(False)
+    scheme = parse_scheme("W4A16", {"group_size": -1})
+    q = SignRoundQuantizer(scheme, iters=iters, batch_size=4)
+    q.quantize_block(blk, [t.to(DEV) for t in b["inputs"]], b["others"], [t.to(DEV) for t in b["fp_outputs"]], None, None,
+                     input_ids=b["input_ids"], sampler=S.ReplaySampler(ores.batches))
+    res = q.last_result
+    assert res.losses[0] == pytest.approx(ores.losses[0], rel=2e-2)
+    g_mse = _block_mse(blk, b["inputs"], b["others"], b["fp_outputs"], masks, DEV)
+    assert g_mse == pytest.approx(o_mse, rel=0.25), (g_mse, o_mse)
+    from auto_round_b200 import export
+    from oracle import pack as P
+    lin = blk.self_attn.q_proj
+    assert tuple(lin.scale.shape) == (lin.weight.shape[0], 1)
+    wq, sc = lin.weight.data.clone(), lin.scale.clone()
+    ql = export.pack_linear(lin, scheme, DEV)
+    want = P.pack_int(wq.cpu(), sc.cpu().reshape(wq.shape[0], -1), 8, 4, wq.shape[1], zp_minus_one=True)
+    import numpy as np
+    assert np.array_equal(ql.qweight.numpy(), want["qweight"]) and np.array_equal(ql.scales.numpy(), want["scales"])

@@ -30,6 +30,9 @@ CASES = [  # name, qdq name, bits, g, n, k, with init (alg_ext)
     ("int_sym_w4g128_kpad", "int_sym", 4, 128, 16, 200, False),
     ("int_sym_w2g32_init", "int_sym", 2, 32, 16, 256, True), ("mx_fp4_init", "mx_fp4", 4, 32, 16, 256, True),
     ("nv_fp4_init", "nv_fp4", 4, 16, 16, 256, True),
+    # per-row groups: group_size = -1, and a weight narrower than the group (data_type/utils.py:57-61)
+    ("int_sym_w4_row", "int_sym", 4, -1, 24, 512, False), ("int_asym_w8_row", "int_asym", 8, -1, 16, 1024, False),
+    ("int_sym_w4_k_lt_g", "int_sym", 4, 128, 16, 64, False),
 ]
 
 
@@ -128,7 +131,7 @@ def test_fused_update_matches_oracle(name, qname, bits, g, n, k, with_init):
     wq_own, _, _ = _oracle_qdq(qname, w, bits, g, d["v"].cpu().reshape(v.shape), mn_dev, d["mx"].cpu(), init, gs)
     assert torch.equal(d["wq"].cpu(), wq_own.to(w.dtype)), name
     # ... and to the oracle's own step wherever the scale parameters agree
-    gpr = spec.kpad // g
+    gpr = spec.kpad // spec.group_size
     rows_ok = same.reshape(n, gpr).all(dim=1)
     assert torch.equal(d["wq"].cpu()[rows_ok], wq2[rows_ok])
 
@@ -178,3 +181,28 @@ def test_fused_update_row_shards_equal_full(name, qname, bits, g, n, k, with_ini
     for key in ("v", "mx", "mn", "wq", "best_v", "best_mx"):
         if full[key] is not None:
             assert torch.equal(full[key], sh[key]), key
+
+
+@pytest.mark.parametrize("qname,bits,g,n,k", [("int_sym", 4, -1, 24, 512), ("int_asym", 2, -1, 16, 256), ("int_sym", 8, 128, 8, 64)])
+def test_per_row_groups_forward_bit_exact(qname, bits, g, n, k):
+    """group_size = -1 / K < group_size: one group per row -- group min/max, fake-quant weight, scale and zero-point bit-exact
+    to the oracle (RTN form and with V / min_scale / max_scale)."""
+    gen = torch.Generator().manual_seed(n + k)
+    w = (torch.randn(n, k, generator=gen) * 0.05).bfloat16()
+    spec = ops.make_spec(qname, bits, g, n, k)
+    assert spec.group_size == k and spec.groups == n
+    wmin, wmax = ops.group_minmax(spec, w.to(DEV))
+    rmin, rmax = Q.group_minmax(w, g)
+    assert torch.equal(wmin.cpu(), rmin.reshape(-1)) and torch.equal(wmax.cpu(), rmax.reshape(-1))
+    v = ((torch.rand(n, k, generator=gen) - 0.5) * 0.8).float()
+    mn, mx = (0.5 + 0.5 * torch.rand(n, generator=gen)).float(), (0.5 + 0.5 * torch.rand(n, generator=gen)).float()
+    fn = Q.int_sym if qname == "int_sym" else Q.int_asym
+    ref_q, ref_s, ref_zp = fn(w, bits, g, v, mn, mx)
+    wq, sc, zp = ops.qdq_fwd(spec, w.to(DEV), v.to(DEV), mn.to(DEV), mx.to(DEV), wmin, wmax, None, want_scale=True)
+    assert torch.equal(wq.cpu(), ref_q.to(w.dtype))
+    assert torch.equal(sc.float().cpu().reshape(-1), ref_s.float().reshape(-1))
+    if qname == "int_asym":
+        assert torch.equal(zp.cpu().reshape(-1), ref_zp.float().reshape(-1))
+    ref_q0, ref_s0, _ = fn(w, bits, g)                                    # plain RTN (iters = 0 / unwrap without parameters)
+    wq0, sc0, _ = ops.qdq_fwd(spec, w.to(DEV), want_scale=True)
+    assert torch.equal(wq0.cpu(), ref_q0.to(w.dtype)) and torch.equal(sc0.float().cpu().reshape(-1), ref_s0.float().reshape(-1))
