@@ -42,7 +42,8 @@ SIGNATURES = {
     "ar_fq_linear_fwd": [_QS, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "ar_fq_linear_bwd_dx": [_QS, _P, _L, _P, _P, _P],
     "ar_fq_linear_bwd_dw": [_QS, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
-    "ar_fq_update": [_QS, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _F, _P, _P, _P, _P, _P, _P],
+    "ar_fq_update": [_QS, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P],
+    "ar_wq_decode": [_QS, _P, _L, _I, _P, _P],
     "ar_mse_fwd_bwd": [_P, _P, _P, _L, _L, _F, _F, _P, _P, _P],
     "ar_best_update": [_P, _D, _D, _I, _P, _P, _P, _P, _P, _P],
     "ar_signsgd_step": [_P, _P, _I, _P, _P, _P, _P, _I, _P, _L, _L, _F, _P],

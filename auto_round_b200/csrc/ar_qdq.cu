@@ -316,6 +316,10 @@ struct UpdArgs {
   const int32_t* it_ptr;
   float clamp_hi;
   uint16_t* wq;            // out bf16 [N, K]
+  // data-parallel wire form of the shard's new Wq (instead of `wq`): one u32 of eight 4-bit codes per chunk, indexed from row
+  // row0, and {a, off} per group -- ar_wq_decode rebuilds bf16(a * (code - off)) (fp4: a * e2m1(code)) on every rank
+  uint32_t* codes;
+  float2* gparams;
   float* dv_dbg;           // optional pre-sign gradients (tests): [N, kpad], [G], [G]
   float* dmn_dbg;
   float* dmx_dbg;
@@ -404,6 +408,18 @@ __global__ void __launch_bounds__(kThreads) fq_update_kernel(QArgs a, UpdArgs u)
   }
   // next iteration's fake-quant weight
   ctx.setup(gi);
+  if (u.codes != nullptr) {                          // 4-bit wire codes + group parameters; the decode kernel writes Wq
+    uint32_t word = 0u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) word |= (ctx.enc(w[i], v[i]) & 15u) << (4 * i);
+    u.codes[(int64_t)(n - u.row0) * cpr + k0 / 8] = word;
+    if (lead) {
+      float pa, po;
+      ctx.dec_params(pa, po);
+      u.gparams[(int64_t)(n - u.row0) * (a.kpad / G) + k0 / G] = make_float2(pa, po);
+    }
+    return;
+  }
   uint32_t packed[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -417,6 +433,36 @@ __global__ void __launch_bounds__(kThreads) fq_update_kernel(QArgs a, UpdArgs u)
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       if (k0 + i < a.k) u.wq[(int64_t)n * a.k + k0 + i] = (uint16_t)((packed[i / 2] >> (16 * (i & 1))) & 0xffffu);
+  }
+}
+
+// Rebuild the bf16 fake-quant weight of a whole layer from the all-gathered wire segments: rank r's segment holds the codes
+// (u32 per 8 elements) and then the {a, off} pairs of its rows [r * rows_per_rank, (r + 1) * rows_per_rank).
+__global__ void __launch_bounds__(kThreads) wq_decode_kernel(const uint8_t* __restrict__ seg_all, int64_t seg_bytes,
+                                                            int rows_per_rank, int n, int k, int kpad, int g, int is_fp4,
+                                                            uint16_t* __restrict__ wq) {
+  const int cpr = kpad / 8, gpr = kpad / g;
+  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (c >= (int64_t)n * cpr) return;
+  const int row = (int)(c / cpr), k0 = (int)(c % cpr) * 8;
+  const int r = row / rows_per_rank, lrow = row - r * rows_per_rank;
+  const uint8_t* seg = seg_all + (int64_t)r * seg_bytes;
+  const uint32_t word = reinterpret_cast<const uint32_t*>(seg)[(int64_t)lrow * cpr + k0 / 8];
+  const float2 pr = reinterpret_cast<const float2*>(seg + (int64_t)rows_per_rank * cpr * 4)[(int64_t)lrow * gpr + k0 / g];
+  uint32_t packed[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t n0 = (word >> (8 * i)) & 15u, n1 = (word >> (8 * i + 4)) & 15u;
+    const float f0 = is_fp4 ? e2m1_dec(n0) * pr.x : pr.x * ((float)n0 - pr.y);
+    const float f1 = is_fp4 ? e2m1_dec(n1) * pr.x : pr.x * ((float)n1 - pr.y);
+    packed[i] = (uint32_t)f32_to_bf16_bits(f0) | ((uint32_t)f32_to_bf16_bits(f1) << 16);
+  }
+  if ((k % 8) == 0 && k0 + 8 <= k) {
+    *reinterpret_cast<U4*>(wq + (int64_t)row * k + k0) = U4{packed[0], packed[1], packed[2], packed[3]};
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (k0 + i < k) wq[(int64_t)row * k + k0 + i] = (uint16_t)((packed[i / 2] >> (16 * (i & 1))) & 0xffffu);
   }
 }
 
@@ -692,9 +738,13 @@ extern "C" int ar_fq_update(const ar_qspec* q, const void* w, float* v, float* m
                             const void* wmax, const float* gscale, const void* gq, int gq_row0, int row0, int row1,
                             float* best_v, float* best_mn, float* best_mx, const int32_t* flag, const float* lr_table,
                             int iter, const int32_t* it_ptr, float clamp_hi, void* wq_out, float* dv_dbg, float* dmn_dbg,
-                            float* dmx_dbg, const int32_t* has_grad, void* stream) {
+                            float* dmx_dbg, const int32_t* has_grad, void* codes_out, void* gparams_out, void* stream) {
   if (int rc = check_spec(q)) return rc;
-  AR_REQUIRE(w && v && mx && gq && lr_table && wq_out, AR_E_BADARG, "w/v/max_scale/gq/lr_table/wq must be non-null");
+  AR_REQUIRE(w && v && mx && gq && lr_table && (wq_out || codes_out), AR_E_BADARG,
+             "w/v/max_scale/gq/lr_table and wq_out (or codes_out) must be non-null");
+  AR_REQUIRE((codes_out == nullptr) == (gparams_out == nullptr), AR_E_BADARG, "codes_out and gparams_out go together");
+  AR_REQUIRE(codes_out == nullptr || (q->bits <= 4 && !row_mode(q)), AR_E_UNSUPPORTED,
+             "the 4-bit wire form exists for bits <= 4 and grouped (not per-row) layouts");
   AR_REQUIRE((wmin == nullptr) == (wmax == nullptr), AR_E_BADARG, "wmin/wmax must both be given or both null");
   AR_REQUIRE(q->dtype != AR_DT_NV_FP4 || gscale != nullptr, AR_E_BADARG, "nv_fp4 needs gscale");
   AR_REQUIRE(0 <= row0 && row0 <= row1 && row1 <= q->n && gq_row0 <= row0 && iter >= 0, AR_E_BADARG,
@@ -706,6 +756,7 @@ extern "C" int ar_fq_update(const ar_qspec* q, const void* w, float* v, float* m
   u.v = v; u.mn = mn; u.mx = mx; u.best_v = best_v; u.best_mn = best_mn; u.best_mx = best_mx; u.flag = flag;
   u.lr_table = lr_table; u.iter = iter; u.it_ptr = it_ptr; u.clamp_hi = clamp_hi; u.wq = (uint16_t*)wq_out;
   u.dv_dbg = dv_dbg; u.dmn_dbg = dmn_dbg; u.dmx_dbg = dmx_dbg; u.has_grad = has_grad;
+  u.codes = (uint32_t*)codes_out; u.gparams = (float2*)gparams_out;
   cudaStream_t st = (cudaStream_t)stream;
   if (row_mode(q)) {
     const dim3 rgrid((unsigned)((row1 - row0 + kRowWarps - 1) / kRowWarps));
@@ -721,6 +772,22 @@ extern "C" int ar_fq_update(const ar_qspec* q, const void* w, float* v, float* m
   else if (q->dtype == AR_DT_INT_ASYM) launch_upd_g<IntAsym, false>(g, grid, st, a, u);
   else if (q->dtype == AR_DT_MX_FP4) launch_upd_g<MxFp4, true>(g, grid, st, a, u);
   else launch_upd_g<NvFp4, true>(g, grid, st, a, u);
+  AR_CHECK_LAUNCH();
+  return AR_OK;
+}
+
+extern "C" int ar_wq_decode(const ar_qspec* q, const void* segments, int64_t seg_bytes, int world, void* wq_out, void* stream) {
+  if (int rc = check_spec(q)) return rc;
+  AR_REQUIRE(segments && wq_out && world >= 1 && q->n % world == 0, AR_E_BADARG, "ar_wq_decode: bad arguments (rows must split evenly)");
+  AR_REQUIRE(q->bits <= 4 && !row_mode(q), AR_E_UNSUPPORTED, "ar_wq_decode: bits <= 4, grouped layouts");
+  const int g = q->group_size;
+  const int kpad = (q->k + g - 1) / g * g;
+  const int rows = q->n / world;
+  AR_REQUIRE(seg_bytes >= (int64_t)rows * (kpad / 8) * 4 + (int64_t)rows * (kpad / g) * 8, AR_E_BADARG, "ar_wq_decode: segment too small");
+  const int64_t chunks = (int64_t)q->n * (kpad / 8);
+  const int fp4 = (q->dtype == AR_DT_MX_FP4 || q->dtype == AR_DT_NV_FP4) ? 1 : 0;
+  wq_decode_kernel<<<(unsigned)((chunks + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      (const uint8_t*)segments, seg_bytes, rows, q->n, q->k, kpad, g, fp4, (uint16_t*)wq_out);
   AR_CHECK_LAUNCH();
   return AR_OK;
 }

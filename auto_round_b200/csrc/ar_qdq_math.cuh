@@ -89,6 +89,9 @@ struct IntSym {
     return clampf(rintf(div_exact(w, s, rs) + v), -kMaxq, kMaxq - 1.f);
   }
   __device__ __forceinline__ float fwd(float w, float v) const { return s * code(w, v); }
+  // 4-bit wire code of the fake-quant value (data-parallel exchange of the next Wq): fwd == a * (enc - off), bits <= 4
+  __device__ __forceinline__ uint32_t enc(float w, float v) const { return (uint32_t)(int)(code(w, v) + kMaxq); }
+  __device__ __forceinline__ void dec_params(float& a, float& off) const { a = s; off = kMaxq; }
   __device__ __forceinline__ void bwd(float w, float v, float gq, float& dv, GroupAcc& acc) const {
     const float ws = div_exact(w, s, rs);
     const float r = rintf(ws + v);
@@ -126,6 +129,8 @@ struct IntAsym {
     return clampf(rintf(div_exact(w, s, rs) + v) + zp, 0.f, kMaxq);
   }
   __device__ __forceinline__ float fwd(float w, float v) const { return s * (code(w, v) - zp); }
+  __device__ __forceinline__ uint32_t enc(float w, float v) const { return (uint32_t)(int)code(w, v); }
+  __device__ __forceinline__ void dec_params(float& a, float& off) const { a = s; off = zp; }
   __device__ __forceinline__ void bwd(float w, float v, float gq, float& dv, GroupAcc& acc) const {
     const float ws = div_exact(w, s, rs);
     const float u = rintf(ws + v) + zp;
@@ -169,6 +174,18 @@ __device__ __forceinline__ float mx_quant_element(float t) {
   return clampf(r / 2.f * p, -6.f, 6.f);
 }
 
+// E2M1 value (0, +-0.5 .. +-6, signed zero kept) <-> 4-bit wire code: sign << 3 | index into {0, .5, 1, 1.5, 2, 3, 4, 6}
+__device__ __forceinline__ uint32_t e2m1_enc(float val) {
+  const float a2 = fabsf(val) * 2.f;                       // 0 1 2 3 4 6 8 12
+  const uint32_t idx = a2 < 4.5f ? (uint32_t)(int)a2 : (a2 < 7.f ? 5u : (a2 < 10.f ? 6u : 7u));
+  return idx | ((__float_as_uint(val) >> 31) << 3);
+}
+__device__ __forceinline__ float e2m1_dec(uint32_t nib) {
+  const uint32_t i = nib & 7u;
+  const float mag = i < 5u ? 0.5f * (float)i : (i == 5u ? 3.f : (i == 6u ? 4.f : 6.f));
+  return (nib & 8u) ? -mag : mag;
+}
+
 struct MxFp4 {
   __device__ __forceinline__ void init(int) {}
   float s;      // 2^e
@@ -190,6 +207,8 @@ struct MxFp4 {
     const float t = clampf(w * rs + v, -6.f, 6.f);
     return mx_quant_element(t) * s;
   }
+  __device__ __forceinline__ uint32_t enc(float w, float v) const { return e2m1_enc(mx_quant_element(clampf(w * rs + v, -6.f, 6.f))); }
+  __device__ __forceinline__ void dec_params(float& a, float& off) const { a = s; off = 0.f; }
   __device__ __forceinline__ void bwd(float w, float v, float gq, float& dv, GroupAcc& acc) const {
     const float ws = w * rs;
     const float t = ws + v;
@@ -249,6 +268,8 @@ struct NvFp4 {
     const float x = clampf(w * inv + v, -6.f, 6.f);
     return nv_cast_to_fp4(x) * rinv;
   }
+  __device__ __forceinline__ uint32_t enc(float w, float v) const { return e2m1_enc(nv_cast_to_fp4(clampf(w * inv + v, -6.f, 6.f))); }
+  __device__ __forceinline__ void dec_params(float& a, float& off) const { a = rinv; off = 0.f; }
   __device__ __forceinline__ void bwd(float w, float v, float gq, float& dv, GroupAcc& acc) const {
     const float x = w * inv + v;
     const bool in = (x >= -6.f) && (x <= 6.f);

@@ -218,12 +218,13 @@ def fq_linear_bwd_dw(spec: Spec, dy2d, x2d, w, v, min_scale, max_scale, wmin, wm
 
 def fq_update(spec: Spec, w, v, min_scale, max_scale, wmin, wmax, gscale, gq, wq_out, lr_table, best_v=None, best_min=None,
               best_max=None, flag=None, it=0, it_dev=None, clamp_hi=1.0, row0=0, row1=None, gq_row0=0, init_scale=None,
-              dbg=None, has_grad=None):
+              dbg=None, has_grad=None, wire=None):
     """Fused per-layer update (include/ar_b200.h ar_fq_update): qdq backward from the bf16 dWq `gq`, snapshot, sign-SGD
     step, next iteration's fake-quant weight into `wq_out` -- rows [row0, row1).  `dbg` = (dv, dmin, dmax) fp32 outputs."""
     _want(w, torch.bfloat16, "w")
     _want(gq, torch.bfloat16, "gq")
-    _want(wq_out, torch.bfloat16, "wq_out")
+    if wq_out is not None:
+        _want(wq_out, torch.bfloat16, "wq_out")
     for t, nm in ((v, "v"), (min_scale, "min_scale"), (max_scale, "max_scale"), (best_v, "best_v"), (lr_table, "lr_table")):
         _want(t, torch.float32, nm)
     row1 = spec.n if row1 is None else row1
@@ -231,10 +232,40 @@ def fq_update(spec: Spec, w, v, min_scale, max_scale, wmin, wmax, gscale, gq, wq
         raise ValueError("gq does not cover rows [gq_row0, row1)")
     cs = _cspec(spec, init_scale)
     dv, dmn, dmx = dbg if dbg is not None else (None, None, None)
+    codes = gpar = None
+    if wire is not None:                      # uint8 segment of this rank: [codes | group params] (wire_segment_bytes)
+        rows = row1 - row0
+        nb = rows * (spec.kpad // 8) * 4
+        if wire.dtype != torch.uint8 or wire.numel() < wire_segment_bytes(spec, rows):
+            raise ValueError("wire segment too small")
+        codes, gpar = wire[:nb], wire[nb:]
     _check(_lib.load().ar_fq_update(C.byref(cs), _p(w), _p(v), _p(min_scale), _p(max_scale), _p(wmin), _p(wmax), _p(gscale),
                                     _p(gq), int(gq_row0), int(row0), int(row1), _p(best_v), _p(best_min), _p(best_max),
-                                    _p(flag), _p(lr_table), int(it), _p(it_dev), float(clamp_hi), _p(wq_out), _p(dv), _p(dmn),
-                                    _p(dmx), _p(has_grad), _stream()), "ar_fq_update")
+                                    _p(flag), _p(lr_table), int(it), _p(it_dev), float(clamp_hi),
+                                    _p(wq_out) if wire is None else None, _p(dv), _p(dmn),
+                                    _p(dmx), _p(has_grad), _p(codes), _p(gpar), _stream()), "ar_fq_update")
+
+
+def wire_supported(spec: Spec) -> bool:
+    """The 4-bit wire form of the next fake-quant weight (data-parallel all-gather): bits <= 4, grouped (not per-row)."""
+    return spec.bits <= 4 and spec.group_size in (16, 32, 64, 128, 256)
+
+
+def wire_segment_bytes(spec: Spec, rows: int) -> int:
+    """One rank's segment: u32 per 8 elements + {a, off} fp32 per group, rounded up to 16 bytes."""
+    nb = rows * (spec.kpad // 8) * 4 + rows * (spec.kpad // spec.group_size) * 8
+    return (nb + 15) // 16 * 16
+
+
+def wq_decode(spec: Spec, segments, world, wq_out):
+    """wq_out[N,K] <- the all-gathered wire segments (uint8 [world * seg_bytes]); bit-identical to fq_update's wq_out."""
+    _want(wq_out, torch.bfloat16, "wq_out")
+    if segments.dtype != torch.uint8 or segments.numel() % world:
+        raise ValueError("segments: uint8, world equal parts")
+    cs = spec.c()
+    _check(_lib.load().ar_wq_decode(C.byref(cs), _p(segments), segments.numel() // world, int(world), _p(wq_out), _stream()),
+           "ar_wq_decode")
+    return wq_out
 
 
 def mse_fwd_bwd(pred2d, ref2d, row_mask, inv_numel, upstream, loss_sum, dpred=None, want_grad=True):

@@ -505,13 +505,18 @@ class SignRoundQuantizer:
         compute_stream = lambda: torch.cuda.current_stream(device)          # noqa: E731 (the capture stream while capturing)
         comm = torch.cuda.Stream(device=device) if dp.world > 1 else None
         best_of = {n: arena.best_views(n) for n in wrapped}
-        shards, gq_shard = {}, {}
+        shards, gq_shard, wire_full, wire_seg = {}, {}, {}, {}
         for n, wl in wrapped.items():
             wl.refresh_wq()                                         # iteration 0 runs on qdq(W; V = 0, scales = 1)
             shards[n] = None if id(wl) in ep_owned else dp.row_shard(wl.spec.n)
             if shards[n] is not None:
                 r0, r1 = shards[n]
                 gq_shard[n] = torch.empty(r1 - r0, wl.spec.k, dtype=torch.bfloat16, device=device)
+                if ops.wire_supported(wl.spec):
+                    # the new fake-quant rows travel as 4-bit codes + per-group {a, off} (a quarter of the bf16 bytes);
+                    # every rank rebuilds the identical bf16 weight with ar_wq_decode
+                    wire_seg[n] = ops.wire_segment_bytes(wl.spec, r1 - r0)
+                    wire_full[n] = torch.zeros(dp.world * wire_seg[n], dtype=torch.uint8, device=device)
         name_of = {id(wl): n for n, wl in wrapped.items()}
 
         def update_layer(wl, grad_flag=None):
@@ -535,8 +540,15 @@ class SignRoundQuantizer:
                 else:
                     r0, r1 = shards[n]
                     dp.reduce_scatter_(gq_shard[n], wl.gq)
-                    ops.fq_update(*args, gq_shard[n], wl.wq, lr_tab, row0=r0, row1=r1, gq_row0=r0, **kw)
-                    dp.all_gather_(wl.wq, wl.wq[r0:r1])
+                    if n in wire_full:
+                        seg = wire_seg[n]
+                        own = wire_full[n][dp.rank * seg:(dp.rank + 1) * seg]
+                        ops.fq_update(*args, gq_shard[n], None, lr_tab, row0=r0, row1=r1, gq_row0=r0, wire=own, **kw)
+                        dp.all_gather_(wire_full[n], own)
+                        ops.wq_decode(wl.spec, wire_full[n], dp.world, wl.wq)
+                    else:
+                        ops.fq_update(*args, gq_shard[n], wl.wq, lr_tab, row0=r0, row1=r1, gq_row0=r0, **kw)
+                        dp.all_gather_(wl.wq, wl.wq[r0:r1])
 
         for wl in wrapped.values():
             wl.on_grad = update_layer

@@ -191,14 +191,24 @@ int ar_fq_linear_bwd_dw(const ar_qspec* q, const void* dy_bf16, const void* x_bf
  *   -> wq_out rows = qdq(W; V', scales') for the next iteration's GEMMs          (WrapperLinear._qdq_weight)
  * v [N,Kpad], min_scale (NULL for mx/nv), max_scale [G] are updated in place; gq is indexed from row gq_row0 (a rank's
  * shard buffer starts at its first row).  dv_dbg/dmn_dbg/dmx_dbg (optional) receive the pre-sign gradients.
- * has_grad (optional, device): *has_grad == 0 leaves the layer untouched (an expert no token was routed to gets no
- * gradient and SignSGD skips it, sign_sgd.py:274-276).
+ * has_grad (optional, device): *has_grad == 0 means the layer received no gradient (an expert no token was routed to):
+ * SignSGD skips it (sign_sgd.py:274-276), only the best-parameter snapshot still includes it.
+ * codes_out / gparams_out (optional, both or none; bits <= 4, not per-row): instead of wq_out the shard's new fake-quant
+ * weight leaves in WIRE form for the data-parallel all-gather -- one u32 of eight 4-bit codes per 8 elements (indexed from
+ * row0) and {a, off} fp32 per group -- a quarter of the bf16 bytes; ar_wq_decode rebuilds the identical bf16 weight.
  */
 int ar_fq_update(const ar_qspec* q, const void* w_bf16, float* v, float* min_scale, float* max_scale,
                  const void* wmin_bf16, const void* wmax_bf16, const float* gscale, const void* gq_bf16, int gq_row0,
                  int row0, int row1, float* best_v, float* best_min_scale, float* best_max_scale, const int32_t* flag,
                  const float* lr_table, int iter, const int32_t* it_ptr, float clamp_hi, void* wq_out_bf16,
-                 float* dv_dbg, float* dmn_dbg, float* dmx_dbg, const int32_t* has_grad, void* stream);
+                 float* dv_dbg, float* dmn_dbg, float* dmx_dbg, const int32_t* has_grad, void* codes_out, void* gparams_out,
+                 void* stream);
+/*
+ * wq_out[N,K] (bf16) from `world` all-gathered wire segments of seg_bytes each: segment r = [codes of rows r*N/world ..
+ * | {a, off} pairs of those rows]; value = bf16(a * (code - off)) for the int types, bf16(a * e2m1(code)) for MXFP4 / NVFP4 --
+ * bit-identical to the wq_out ar_fq_update would have written.
+ */
+int ar_wq_decode(const ar_qspec* q, const void* segments, int64_t seg_bytes, int world, void* wq_out_bf16, void* stream);
 
 /*
  * Masked MSE + its gradient in one pass (auto_round/.../sign_round/quantizer.py:127-158, :789-803):

@@ -2,13 +2,14 @@
 // (g++, no nvcc, no GPU) behind a C entry point, so that the fake-quant forward/backward formulas -- including the
 // enable_alg_ext init_scale branches that have not run on hardware yet -- can be checked against the oracle in the CPU
 // test tier.  The CUDA headers provide host versions of the fp16 / bf16 / e4m3 conversions; the only shims are
-// __uint_as_float and __fmaf_rn.  Group handling mirrors qdq_fwd_kernel / qdq_bwd_kernel (ar_qdq.cu): wmin/wmax clamped at 0, fp4 amax,
+// __uint_as_float, __float_as_uint and __fmaf_rn.  Group handling mirrors qdq_fwd_kernel / qdq_bwd_kernel (ar_qdq.cu): wmin/wmax clamped at 0, fp4 amax,
 // sequential (not shuffle-tree) group sums.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 #include "../../auto_round_b200/csrc/ar_qdq_math.cuh"
 
 namespace {

@@ -206,3 +206,35 @@ def test_per_row_groups_forward_bit_exact(qname, bits, g, n, k):
     ref_q0, ref_s0, _ = fn(w, bits, g)                                    # plain RTN (iters = 0 / unwrap without parameters)
     wq0, sc0, _ = ops.qdq_fwd(spec, w.to(DEV), want_scale=True)
     assert torch.equal(wq0.cpu(), ref_q0.to(w.dtype)) and torch.equal(sc0.float().cpu().reshape(-1), ref_s0.float().reshape(-1))
+
+
+@pytest.mark.parametrize("name,qname,bits,g,n,k,with_init", [c for c in CASES if c[3] > 0 and c[2] <= 4 and c[5] >= c[3]])
+def test_wire_form_decodes_to_the_same_weight(name, qname, bits, g, n, k, with_init):
+    """Data-parallel exchange of the next fake-quant weight as 4-bit codes + per-group {a, off}: the decode kernel must
+    rebuild, bit for bit (signed zeros included), the bf16 weight the plain path writes."""
+    w, v, mn, mx, init, gs, gq, hi = _case(qname, bits, g, n, k, with_init, seed=23)
+    w[3, :8] = 0                                     # zeros (and -0 after rounding) must survive the wire
+    spec = ops.make_spec(qname, bits, g, n, k, 1e-5, hi)
+    assert ops.wire_supported(spec)
+    lr_tab = torch.tensor([9.0, 9.0, 0.004, 0.003], device=DEV)
+    flag = torch.ones(1, dtype=torch.int32, device=DEV)
+    full = _device_state(spec, w, v, mn, mx, init, gs, gq)
+    _run(spec, full, lr_tab, flag, hi)
+    world = 4
+    per = n // world
+    seg = ops.wire_segment_bytes(spec, per)
+    wire = torch.zeros(world * seg, dtype=torch.uint8, device=DEV)
+    sh = _device_state(spec, w, v, mn, mx, init, gs, gq)
+    for r in range(world):
+        r0, r1 = r * per, (r + 1) * per
+        ops.fq_update(spec, sh["w"], sh["v"], sh["mn"], sh["mx"], sh["wmin"], sh["wmax"], sh["gs"], sh["gq"][r0:r1].contiguous(), None,
+                      lr_tab, best_v=sh["best_v"], best_min=sh["best_mn"], best_max=sh["best_mx"], flag=flag, it=1, clamp_hi=hi,
+                      init_scale=sh["init"], row0=r0, row1=r1, gq_row0=r0, wire=wire[r * seg:(r + 1) * seg])
+    out = torch.zeros(n, k, dtype=torch.bfloat16, device=DEV)
+    ops.wq_decode(spec, wire, world, out)
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int16), full["wq"].view(torch.int16)), name        # bit patterns, not values
+    for key in ("v", "mx", "mn", "best_v"):
+        if full[key] is not None:
+            assert torch.equal(full[key], sh[key]), key
+    assert seg * world < n * k * 2 * (0.5 if g >= 32 else 0.8)                          # what the exchange saves
