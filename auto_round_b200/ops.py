@@ -258,7 +258,7 @@ def wire_segment_bytes(spec: Spec, rows: int) -> int:
 
 
 def wq_decode(spec: Spec, segments, world, wq_out):
-    """wq_out[N,K] <- the all-gathered wire segments (uint8 [world * seg_bytes]); bit-identical to fq_update's wq_out."""
+    """wq_out[N,K] <- the all-gathered wire segments (uint8 [world * seg_bytes]); the values fq_update's wq_out would hold."""
     _want(wq_out, torch.bfloat16, "wq_out")
     if segments.dtype != torch.uint8 or segments.numel() % world:
         raise ValueError("segments: uint8, world equal parts")

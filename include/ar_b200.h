@@ -206,7 +206,7 @@ int ar_fq_update(const ar_qspec* q, const void* w_bf16, float* v, float* min_sca
 /*
  * wq_out[N,K] (bf16) from `world` all-gathered wire segments of seg_bytes each: segment r = [codes of rows r*N/world ..
  * | {a, off} pairs of those rows]; value = bf16(a * (code - off)) for the int types, bf16(a * e2m1(code)) for MXFP4 / NVFP4 --
- * bit-identical to the wq_out ar_fq_update would have written.
+ * the same values ar_fq_update would have written to wq_out (int sym: a zero comes back as +0 where s * (-0) gave -0).
  */
 int ar_wq_decode(const ar_qspec* q, const void* segments, int64_t seg_bytes, int world, void* wq_out_bf16, void* stream);
 
