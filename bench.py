@@ -337,7 +337,7 @@ def run_ours(args):
             except Exception as e:  # noqa: BLE001
                 line["per_block_mse_vs_ref"] = {"error": repr(e)[:300]}
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(cfg, steps=3, warmup=1, budget_s=args.cpu_budget)
+            line["cpu_baseline"] = cpu_baseline(cfg, steps=8, warmup=1, budget_s=args.cpu_budget)
     else:
         line["roofline"] = {"bound": "tensor", "note": "measured at N=1 (same kernels); see the N=1 line"}
     print(json.dumps(line), flush=True)
@@ -619,11 +619,13 @@ def _cpu_block(cfg):
 
 def cpu_steps(cfg, steps, warmup, budget_s, threads=None):
     """The reference's algorithm on the host cores: oracle/signround.py BlockTuner (CPU restatement pinned bit-exact to the
-    reference) on ONE full-shape block, wrapper built once.  A STEP is one whole sign-SGD iteration (forward, loss, autograd
-    backward through the fake-quant graph, sign-SGD update of every layer) on a bounded token sample: steps alternate
-    between T_small and T_large = 4 T_small tokens, which separates the weight-sized cost `a` (fake-quant forward/backward and
-    update of 218 M weights: independent of the batch) from the per-token cost `b` (GEMMs, attention): t(T) = a + b T.
-    The metric is then extrapolated: blocks x iters x (a + b x 16384 tokens).  Full-set forwards and pack are not included."""
+    reference) on ONE full-shape block.  A whole sign-SGD iteration of that block costs ~40 s of weight-sized work on 128
+    cores before a single token is processed, so a STEP is a bounded sample of it: one sign-SGD iteration (forward of the whole
+    block, loss, autograd backward, sign-SGD update) in which ONE of the block's linears is tuned (the steps rotate over the
+    seven), on T_small = 256 or T_large = 1024 tokens (alternating).  Fit: t(layer l, T) = a_l + b T, a_l = weight-sized cost of layer l
+    (fake-quant forward/backward + update of its weights), b = per-token cost (GEMMs, attention).  One full iteration is then
+    sum_l a_l + b * 16384 tokens and the metric extrapolates it: blocks x iters x that.  Wrappers are built before the timed
+    region.  Full-set forwards and pack are not included."""
     from oracle import signround as S
 
     if threads is None:
@@ -638,56 +640,74 @@ def cpu_steps(cfg, steps, warmup, budget_s, threads=None):
     c, blk, rot = _cpu_block(cfg)
     name, bits, g = cfg["spec"]
     osc = S.LayerScheme(bits, g, name != "int_asym", {"int_sym": "int", "int_asym": "int", "mx_fp4": "mx_fp", "nv_fp4": "nv_fp"}[name])
-    t_small = 64
+    lin_names = [n for n, m in blk.named_modules() if type(m) is torch.nn.Linear]
+    weights = {n: blk.get_submodule(n).weight.numel() for n in lin_names}
+    order = sorted(lin_names, key=lambda n: weights[n])                      # cheap layers first: the fit needs every layer once
+    t_small = 256
     sizes = [t_small, 4 * t_small]
     n_total = steps + warmup
-    xs, refs, others_by = [], [], {}
-    for i in range(n_total):
-        T = sizes[i % 2]
-        xs.append(torch.randn(1, T, c.hidden_size).to(torch.bfloat16) * 0.02)
-    inputs, fp_out, pos_emb = [], [], []
-    with torch.no_grad():
-        for x in xs:
-            pos = torch.arange(x.shape[1]).unsqueeze(0)
-            cos, sin = rot(x, pos)
-            pe = (cos.to(torch.bfloat16), sin.to(torch.bfloat16))
-            pos_emb.append(pe)
-            fp_out.append(S.block_forward(blk, x, {"position_embeddings": pe, "position_ids": pos}))
-    # per-sample position embeddings differ in length: hand them over as per-sample lists through a tiny sampler-driven shim
-    tuner = S.BlockTuner(blk, xs, {"attention_mask": None}, fp_out, lambda n, m: osc, iters=max(cfg["iters"], n_total), batch_size=1,
-                         lr=1.0 / cfg["iters"], sampler=S.ReplaySampler([[i] for i in range(n_total)]))
-    times, t_begin = [], time.time()
-    for i in range(n_total):
-        pos = torch.arange(xs[i].shape[1]).unsqueeze(0)
-        tuner.others = {"attention_mask": None, "position_embeddings": [pos_emb[i]], "position_ids": [pos]}
+    tuners = {}
+
+    def tuner_for(layer):                                                    # built outside the timed steps
+        if layer not in tuners:
+            b2 = copy.deepcopy(blk)
+            tuners[layer] = S.BlockTuner(b2, [], {"attention_mask": None}, [], lambda n, m, L=layer: osc if n == L else None,
+                                         iters=max(cfg["iters"], n_total + 1), batch_size=1, lr=1.0 / cfg["iters"],
+                                         sampler=S.ReplaySampler([[0]] * (n_total + 1)))
+        return tuners[layer]
+
+    data = {}
+    for T in sizes:
+        x = torch.randn(1, T, c.hidden_size).to(torch.bfloat16) * 0.02
+        pos = torch.arange(T).unsqueeze(0)
+        cos, sin = rot(x, pos)
+        pe = (cos.to(torch.bfloat16), sin.to(torch.bfloat16))
+        with torch.no_grad():
+            ref = S.block_forward(blk, x, {"position_embeddings": pe, "position_ids": pos})
+        data[T] = (x, ref, {"attention_mask": None, "position_embeddings": [pe], "position_ids": [pos]})
+    plan = [(order[i % len(order)], sizes[i % 2]) for i in range(n_total)]     # 7 layers x 2 sizes: all 14 pairs in 14 steps
+    for layer in {p[0] for p in plan}:
+        tuner_for(layer)
+    rows, t_begin = [], time.time()
+    for i, (layer, T) in enumerate(plan):
+        tn = tuner_for(layer)
+        x, ref, others = data[T]
+        tn.inputs, tn.fp_outputs, tn.others = [x], [ref], others
         t0 = time.perf_counter()
-        tuner.step(i)
-        times.append((xs[i].shape[1], time.perf_counter() - t0))
-        if i >= warmup + 1 and (time.time() - t_begin) > budget_s and len(times) - warmup >= 2:
+        tn.step(len(tn.res.losses))
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            rows.append((layer, T, dt))
+        if i >= warmup and (time.time() - t_begin) > budget_s and len(rows) >= 2:
             break
-    timed = times[warmup:]
-    sm = [t for T, t in timed if T == sizes[0]]
-    lg = [t for T, t in timed if T == sizes[1]]
-    if sm and lg:
-        ts, tl = sum(sm) / len(sm), sum(lg) / len(lg)
-        b = max((tl - ts) / (sizes[1] - sizes[0]), 0.0)
-        a = max(ts - b * sizes[0], 0.0)
-    else:                                   # a single size was timed: everything attributed to the tokens (upper bound)
-        allt = sm or lg
-        T0 = sizes[0] if sm else sizes[1]
-        a, b = 0.0, (sum(allt) / len(allt)) / T0
-    per_iter = a + b * (BATCH * SEQLEN)
+    # least squares for a_l (one per layer seen) and b
+    seen = sorted({r[0] for r in rows}, key=lambda n: weights[n])
+    import numpy as np
+    A = np.zeros((len(rows), len(seen) + 1))
+    y = np.zeros(len(rows))
+    for j, (layer, T, dt) in enumerate(rows):
+        A[j, seen.index(layer)] = 1.0
+        A[j, -1] = T
+        y[j] = dt
+    sol, *_ = np.linalg.lstsq(A, y, rcond=None)
+    a = {n: max(float(sol[k]), 0.0) for k, n in enumerate(seen)}
+    b = max(float(sol[-1]), 0.0) if len({r[1] for r in rows}) > 1 else 0.0
+    # layers never timed (run cut short by the budget): scale the measured weight-sized cost by the weight count
+    per_weight = sum(a.values()) / max(sum(weights[n] for n in seen), 1)
+    a_total = sum(a.get(n, per_weight * weights[n]) for n in lin_names)
+    per_iter = a_total + b * (BATCH * SEQLEN)
     total_s = per_iter * cfg["iters"] * cfg["n_blocks"]
-    step_ms = 1e3 * sum(t for _, t in timed) / max(len(timed), 1)
-    return {"value": round(total_s, 1), "unit": "s", "cores": cores, "kind": "port", "ms_per_step": round(step_ms, 1), "steps_timed": len(timed),
-            "fit": {"weight_sized_s_per_iter": round(a, 3), "s_per_token_per_iter": round(b, 6), "s_per_full_iteration": round(per_iter, 2)},
-            "sample": "oracle/signround.py BlockTuner (CPU restatement pinned bit-exact to the reference; wrapper built once) on ONE "
-                      "full-shape block; each step = one whole sign-SGD iteration on %d or %d tokens (alternating); fit t = a + b T, "
-                      "extrapolated to 8x2048 tokens x %d iters x %d blocks; EXTRAPOLATED, full-set forwards and pack not included; "
-                      "nproc=%d" % (sizes[0], sizes[1], cfg["iters"], cfg["n_blocks"], cores)}
+    step_ms = 1e3 * sum(r[2] for r in rows) / max(len(rows), 1)
+    return {"value": round(total_s, 1), "unit": "s", "cores": cores, "kind": "port", "ms_per_step": round(step_ms, 1), "steps_timed": len(rows),
+            "fit": {"weight_sized_s_per_iter": round(a_total, 3), "s_per_token_per_iter": round(b, 6), "s_per_full_iteration": round(per_iter, 2),
+                    "layers_timed": len(seen), "layers": len(lin_names)},
+            "sample": "oracle/signround.py BlockTuner (CPU restatement pinned bit-exact to the reference; wrappers built before the timed steps) on "
+                      "ONE full-shape block; each step = one sign-SGD iteration with ONE linear tuned (rotating over the block's %d) on %d or %d "
+                      "tokens; fit t = a_layer + b T; one iteration = sum a_layer + b x 16384 tokens; x %d iters x %d blocks; EXTRAPOLATED, "
+                      "full-set forwards and pack not included; nproc=%d" % (len(lin_names), sizes[0], sizes[1], cfg["iters"], cfg["n_blocks"], cores)}
 
 
-def cpu_baseline(cfg, steps=3, warmup=1, budget_s=40.0):
+def cpu_baseline(cfg, steps=8, warmup=1, budget_s=40.0):
     return cpu_steps(cfg, steps, warmup, budget_s)
 
 
@@ -697,7 +717,7 @@ def run_reference(args):
         return
     cfg = CONFIGS[args.config]
     iters = args.iters if args.iters else cfg["iters"]
-    cb = cpu_steps(cfg, max(args.steps, 2), max(args.warmup, 1), budget_s=150.0)
+    cb = cpu_steps(cfg, max(args.steps, 2), max(args.warmup, 0), budget_s=240.0)
     line = {"impl": "reference", "metric": cfg["metric"], "value": cb["value"], "unit": "s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
