@@ -622,7 +622,7 @@ def cpu_steps(cfg, steps, warmup, budget_s, threads=None):
     reference) on ONE full-shape block.  A whole sign-SGD iteration of that block costs ~40 s of weight-sized work on 128
     cores before a single token is processed, so a STEP is a bounded sample of it: one sign-SGD iteration (forward of the whole
     block, loss, autograd backward, sign-SGD update) in which ONE of the block's linears is tuned (the steps rotate over the
-    seven), on T_small = 256 or T_large = 1024 tokens (alternating).  Fit: t(layer l, T) = a_l + b T, a_l = weight-sized cost of layer l
+    seven), on T_small = 128 or T_large = 512 tokens (alternating).  Fit: t(layer l, T) = a_l + b T, a_l = weight-sized cost of layer l
     (fake-quant forward/backward + update of its weights), b = per-token cost (GEMMs, attention).  One full iteration is then
     sum_l a_l + b * 16384 tokens and the metric extrapolates it: blocks x iters x that.  Wrappers are built before the timed
     region.  Full-set forwards and pack are not included."""
@@ -643,7 +643,7 @@ def cpu_steps(cfg, steps, warmup, budget_s, threads=None):
     lin_names = [n for n, m in blk.named_modules() if type(m) is torch.nn.Linear]
     weights = {n: blk.get_submodule(n).weight.numel() for n in lin_names}
     order = sorted(lin_names, key=lambda n: weights[n])                      # cheap layers first: the fit needs every layer once
-    t_small = 256
+    t_small = 128
     sizes = [t_small, 4 * t_small]
     n_total = steps + warmup
     tuners = {}
@@ -739,7 +739,7 @@ def main():
     ap.add_argument("--iters", type=int, default=0, help="sign-SGD iterations per block (0: the config's own, metric: 200)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mse-check", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=40.0)
+    ap.add_argument("--cpu-budget", type=float, default=60.0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
