@@ -717,7 +717,7 @@ def run_reference(args):
         return
     cfg = CONFIGS[args.config]
     iters = args.iters if args.iters else cfg["iters"]
-    cb = cpu_steps(cfg, max(args.steps, 2), max(args.warmup, 0), budget_s=240.0)
+    cb = cpu_steps(cfg, max(args.steps, 2), max(args.warmup, 0), budget_s=180.0)
     line = {"impl": "reference", "metric": cfg["metric"], "value": cb["value"], "unit": "s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
