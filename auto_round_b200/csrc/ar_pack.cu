@@ -12,7 +12,10 @@ namespace ar {
 // code of one element: torch.round(W / s + zp).to(int32)   (fp32 division after bf16/fp16 promotion)
 __device__ __forceinline__ int32_t int_code(float w, float s, float zp) { return (int32_t)rintf(w / s + zp); }
 
-// ---- 2/4/8-bit: tile = 32 rows (n) x 32 words (kw).  blockDim = (32, 8)
+// ---- 2/4/8-bit: tile = 32 rows (n) x 32 words (kw).  blockDim = (32, 8).  A thread builds one output word from PER = 32 / BITS
+// consecutive K-elements of one row: ONE vector load (8 / 16 / 32 B), one scale / zero-point load when the word lies inside
+// a group (every supported group size), and the quotient without div.rn (div_exact: bit-identical to w / s for a bf16 w
+// and an fp16 s with |s| >= 1e-5, tests/test_div_exact.py; any other scale takes the IEEE division).
 template <int BITS>
 __global__ void __launch_bounds__(256) pack_pow2_kernel(const uint16_t* __restrict__ wq, const __half* __restrict__ scale,
                                                         const float* __restrict__ zp, float zp_const, int n, int k,
@@ -22,20 +25,48 @@ __global__ void __launch_bounds__(256) pack_pow2_kernel(const uint16_t* __restri
   const int kw_total = k / PER;
   const int ngroups = (k + group_size - 1) / group_size;
   const int kw = blockIdx.x * 32 + threadIdx.x;
+  const bool one_group = (group_size % PER) == 0;
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int row = blockIdx.y * 32 + r;
     int32_t word = 0;
     if (row < n && kw < kw_total) {
       const int k0 = kw * PER;
       const uint16_t* src = wq + (int64_t)row * k + k0;
-      uint32_t acc = 0;
+      uint16_t e[PER];
+      if (BITS == 8) {
+        const U2 v = *reinterpret_cast<const U2*>(src);
+        e[0] = (uint16_t)(v.x & 0xffffu); e[1] = (uint16_t)(v.x >> 16); e[2] = (uint16_t)(v.y & 0xffffu); e[3] = (uint16_t)(v.y >> 16);
+      } else {
 #pragma unroll
-      for (int j = 0; j < PER; ++j) {
-        const int kk = k0 + j;
-        const int gi = kk / group_size;
-        const float s = __half2float(scale[(int64_t)row * ngroups + gi]);
-        const float z = zp ? zp[(int64_t)row * ngroups + gi] : zp_const;
-        acc += ((uint32_t)int_code(bf16_bits_to_f32(src[j]), s, z)) << (BITS * j);   // sum of shifted lanes, wraps like int32
+        for (int q = 0; q < PER / 8; ++q) {
+          const U4 v = reinterpret_cast<const U4*>(src)[q];
+          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { e[q * 8 + 2 * i] = (uint16_t)(u[i] & 0xffffu); e[q * 8 + 2 * i + 1] = (uint16_t)(u[i] >> 16); }
+        }
+      }
+      uint32_t acc = 0;
+      if (one_group) {
+        const int64_t gidx = (int64_t)row * ngroups + k0 / group_size;
+        const float s = __half2float(scale[gidx]);
+        const float z = zp ? zp[gidx] : zp_const;
+        if (fabsf(s) >= 1e-5f) {
+          const float rs = 1.f / s;
+#pragma unroll
+          for (int j = 0; j < PER; ++j)
+            acc += ((uint32_t)(int32_t)rintf(div_exact(bf16_bits_to_f32(e[j]), s, rs) + z)) << (BITS * j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < PER; ++j) acc += ((uint32_t)int_code(bf16_bits_to_f32(e[j]), s, z)) << (BITS * j);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+          const int gi = (k0 + j) / group_size;
+          const float s = __half2float(scale[(int64_t)row * ngroups + gi]);
+          const float z = zp ? zp[(int64_t)row * ngroups + gi] : zp_const;
+          acc += ((uint32_t)int_code(bf16_bits_to_f32(e[j]), s, z)) << (BITS * j);   // sum of shifted lanes, wraps like int32
+        }
       }
       word = (int32_t)acc;
     }
@@ -176,6 +207,10 @@ __global__ void unpack_int_kernel(const int32_t* __restrict__ qweight, const int
 // ---- FP4: nibble = first-argmin over {0,.5,1,1.5,2,3,4,6} | signbit<<3 ; low nibble = even k
 template <bool IN_BF16_MATH>
 __device__ __forceinline__ uint32_t e2m1_nibble(float x) {
+  // a value that already IS an E2M1 number (every weight that comes out of the fake-quant functions) has distance 0 to exactly
+  // one table entry: that index is the first argmin -- no search needed
+  const uint32_t direct = e2m1_enc(x);
+  if (e2m1_dec(direct) == x) return direct;
   const float lut[8] = {0.f, 0.5f, 1.f, 1.5f, 2.f, 3.f, 4.f, 6.f};
   const float a = fabsf(x);
   float best = 0.f;
@@ -202,7 +237,17 @@ __global__ void pack_fp4_nv_kernel(const uint16_t* __restrict__ wq, const float*
   const float rg = (gs == 0.f) ? 0.f : 1.f / gs;
   const float prod = sc * rg;
   const float inv = (prod == 0.f) ? 0.f : 1.f / prod;
-  const uint16_t* src = wq + (int64_t)row * k + gi * 16;
+  uint16_t src[16];
+  {
+    const U4* v = reinterpret_cast<const U4*>(wq + (int64_t)row * k + gi * 16);        // 2 x 16 B (k % 16 == 0)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const U4 t = v[q];
+      const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { src[q * 8 + 2 * i] = (uint16_t)(u[i] & 0xffffu); src[q * 8 + 2 * i + 1] = (uint16_t)(u[i] >> 16); }
+    }
+  }
   uint32_t lo = 0, hi = 0;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -224,12 +269,21 @@ __global__ void pack_fp4_mx_kernel(const uint16_t* __restrict__ wq, const uint16
   const int row = (int)(idx / gpr), gi = (int)(idx % gpr);
   const float e = bf16_bits_to_f32(exp_bf16[idx]);
   const float p = bf16_round(exp2f(e));                        // 2 ** scales, bf16 tensor
-  const uint16_t* src = wq + (int64_t)row * k + gi * 32;
+  // p is a power of two for every exponent the quantiser stores: W / p == W * (1 / p) exactly; anything else divides
+  const bool pow2 = (__float_as_uint(p) & 0x007fffffu) == 0u && p != 0.f;
+  const float rp = pow2 ? 1.f / p : 0.f;
+  const U4* v = reinterpret_cast<const U4*>(wq + (int64_t)row * k + gi * 32);          // 4 x 16 B (k % 32 == 0)
   uint32_t o[4] = {0, 0, 0, 0};
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float x = bf16_round(bf16_bits_to_f32(src[j]) / p);
-    o[j / 8] |= e2m1_nibble<true>(x) << (4 * (j % 8));
+  for (int q = 0; q < 4; ++q) {
+    const U4 t = v[q];
+    const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float w = bf16_bits_to_f32((uint16_t)((i & 1) ? (u[i / 2] >> 16) : (u[i / 2] & 0xffffu)));
+      const float x = bf16_round(pow2 ? w * rp : w / p);
+      o[q] |= e2m1_nibble<true>(x) << (4 * i);
+    }
   }
   *reinterpret_cast<U4*>(packed + (int64_t)row * (k / 2) + gi * 16) = U4{o[0], o[1], o[2], o[3]};
   if (scale_e8m0) scale_e8m0[idx] = (uint8_t)clampf(bf16_round(e + 127.f), 0.f, 255.f);
