@@ -4,7 +4,10 @@ tuned (a) by this engine and (b) by the reference's algorithm -- oracle/signroun
 same GPU, the SAME batch sequence.  Bars (the tiny-block tests of test_gpu_engine.py use 2e-2 / +-25 %; at 16384 tokens per
 iteration the sign-SGD trajectories stay together):
   * iteration-0 loss (V = 0: pure RTN forward)              rel <= 1e-3        (measured by the bench at this shape: 1.3e-5)
-  * final block-output MSE vs the FP block                  within +-5 %       (measured: 0.04 % / 0.02 %), both below RTN
+  * final block-output MSE vs the FP block                  within +-5 %       (measured: 0.04 % / 0.007 %), both below RTN;
+                                                             NVFP4: +-8 % (measured -2.3 %: every 16 weights share a tunable scale
+                                                             whose gradient the reference rounds through the scale tensor's dtype
+                                                             while this engine keeps fp32)
   * sign(dV) agreement at iteration 0 (Llama W4A16 case)    >= 97 % of the elements above 5 % of the largest |dV|
 Configs: Llama-3-8B W4A16 g128 (configs[1]), Llama-3-8B W2A16 asym g32 + enable_alg_ext (configs[2], 200 of its 1000
 iterations), Qwen2-7B NVFP4 weight-only (configs[3])."""
@@ -111,7 +114,7 @@ def test_named_shape_block_matches_the_reference_algorithm(case):
     print(f"\\n[{case}] iter0 loss ours {res.losses[0]:.6e} ref {ores.losses[0]:.6e} | final MSE ours {mse_ours:.6e} ref {mse_ref:.6e} "
           f"rtn {mse_rtn:.6e} | best iter {res.best_iter} / {ores.best_iter}")
     assert res.losses[0] == pytest.approx(ores.losses[0], rel=1e-3)
-    assert mse_ours == pytest.approx(mse_ref, rel=0.05), (mse_ours, mse_ref)
+    assert mse_ours == pytest.approx(mse_ref, rel=0.08 if scheme.qdq_name == "nv_fp4" else 0.05), (mse_ours, mse_ref)
     assert mse_ours < mse_rtn and mse_ref < mse_rtn
 
 

@@ -104,3 +104,48 @@ def test_block_snapshot_roundtrip():
     assert torch.equal(o.weight.data, b.attn.o_proj.weight.data) and o.zp == 8
     assert torch.equal(o.scale, b.attn.o_proj.scale) and torch.equal(o.weight_global_scale, torch.tensor([3.5]))
     assert torch.equal(fresh.norm.weight, b.norm.weight)                     # untouched modules stay as loaded
+
+
+def test_restore_block_with_fused_experts_after_unfusing():
+    """snapshots are taken AFTER the experts were un-fused (per-expert layer names), so a freshly loaded block --
+    whose experts are still HF's fused 3-D parameters -- must be un-fused before restore_block can find the layers (what
+    AutoRound.quantize does on resume)."""
+    from auto_round_b200.moe import GroupedExperts, unfuse_experts
+
+    class Fused(nn.Module):
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(1)
+            self.gate_up_proj = nn.Parameter(torch.randn(2, 2 * 16, 8, generator=g).bfloat16())
+            self.down_proj = nn.Parameter(torch.randn(2, 8, 16, generator=g).bfloat16())
+            self.act_fn = nn.SiLU()
+
+    def fresh():
+        b = nn.Module()
+        b.mlp = nn.Module()
+        b.mlp.experts = Fused()
+        return b
+
+    done = fresh()
+    assert unfuse_experts(done) == 1 and isinstance(done.mlp.experts, GroupedExperts)
+    names = [n for n, m in done.named_modules() if type(m) is nn.Linear]
+    assert "mlp.experts.1.down_proj" in names and len(names) == 6
+    for n in names:                                         # stand-in for what the tuner leaves behind
+        lin = done.get_submodule(n)
+        lin.weight.data.mul_(0.5)
+        lin.scale = torch.full((lin.weight.shape[0], 1), 0.25, dtype=torch.bfloat16)
+        lin.zp = None
+    snap = R.snapshot_block(done)
+    assert set(snap) == set(names)
+    again = fresh()
+    with pytest.raises(AttributeError):
+        R.restore_block(again, snap, lambda n, m: parse_scheme("MXFP4", {"act_bits": 16}))     # still fused: no such layers
+    again = fresh()
+    unfuse_experts(again)
+    R.restore_block(again, snap, lambda n, m: parse_scheme("MXFP4", {"act_bits": 16}))
+    for n in names:
+        a, b = again.get_submodule(n), done.get_submodule(n)
+        assert torch.equal(a.weight.data, b.weight.data) and torch.equal(a.scale, b.scale)
+    # the restored weights still alias the stacked tensors the grouped GEMMs read
+    st = again.mlp.experts.stack("down_proj")
+    assert torch.equal(st[1], again.get_submodule("mlp.experts.1.down_proj").weight.data)
