@@ -66,6 +66,24 @@ def _worker(rank, world, port, out):
         dp.all_reduce_(acc, cnt)
         assert float(cnt) == 16.0
         assert torch.allclose(acc / cnt, xs.reshape(-1, 32).pow(2).sum(0) / 16, rtol=1e-6)
+        # the transport calls of the sharded update (gloo emulation of reduce-scatter / all-gather; NCCL on the GPU box):
+        # reduce_scatter_ -> this rank's slice of the SUM; all_gather_ -> every rank's slice, also in place and for the
+        # integer / byte payloads (routing ids, histograms, 4-bit wire segments)
+        full = (torch.arange(8, dtype=torch.float32) + 10 * rank).to(torch.bfloat16)
+        mine = torch.empty(8 // world, dtype=torch.bfloat16)
+        dp.reduce_scatter_(mine, full.clone())
+        want = sum((torch.arange(8, dtype=torch.float32) + 10 * r) for r in range(world))
+        assert torch.equal(mine.float(), want[rank * (8 // world):(rank + 1) * (8 // world)])
+        buf = torch.zeros(8, dtype=torch.bfloat16)
+        buf[rank * 4:(rank + 1) * 4] = torch.tensor([1.5, -2.0, 0.25, 3.0]) * (rank + 1)
+        dp.all_gather_(buf, buf[rank * 4:(rank + 1) * 4])
+        assert buf.tolist() == [1.5, -2.0, 0.25, 3.0, 3.0, -4.0, 0.5, 6.0]
+        for dt in (torch.uint8, torch.int64, torch.int32):
+            seg = torch.full((3,), rank + 7, dtype=dt)
+            allb = torch.zeros(3 * world, dtype=dt)
+            dp.all_gather_(allb, seg)
+            assert allb.tolist() == [7, 7, 7, 8, 8, 8]
+        assert dp.row_shard(8) == (rank * 4, rank * 4 + 4) and dp.row_shard(7) is None and DataParallel().row_shard(8) is None
         out.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         out.put((rank, repr(e)))
